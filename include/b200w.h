@@ -1,0 +1,177 @@
+/* libb200whisper.so -- C ABI of the B200-native Whisper hot path.
+ *
+ * This is the drop-in boundary for the reference's ASR backend.  The reference (pure Python)
+ * reaches its hot path through third-party Python/C++ packages:
+ *   /root/reference/asr_components.py:279-288   self.model.transcribe(...)  -> faster-whisper
+ *        -> FeatureExtractor.__call__ (NumPy log-mel)                       [b200w_logmel*]
+ *        -> WhisperModel.encode -> ctranslate2 Whisper.encode               [b200w_encode]
+ *        -> ctranslate2 Whisper.generate (cross K/V cached at step 0,       [b200w_cross_kv,
+ *           greedy / beam search, logit rules, no_speech_prob)               b200w_decode]
+ *        -> ctranslate2 Whisper.align (cross-attention DTW word timing)      [b200w_align]
+ *        -> ctranslate2 Whisper.detect_language                              [b200w_detect_language]
+ *   /root/reference/audio_deduplicator.py:60-181  _extract_features (NumPy) [b200w_dedup_features]
+ * The Python host side (realtime-whisper-asr_b200/) binds these with ctypes; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions: every function returns 0 on success and -1 on failure (message via
+ * b200w_last_error(), thread-local).  "dev" pointers are CUDA device pointers on the current
+ * device, "host" pointers are ordinary host memory.  `stream` is a cudaStream_t passed as void*
+ * (NULL = default stream).  No CPU fallback exists: without a CUDA device every compute entry
+ * point fails.
+ */
+#ifndef B200W_H_
+#define B200W_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200W_ABI_VERSION 1
+
+const char* b200w_last_error(void);
+int b200w_abi_version(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+uint64_t b200w_launch_count(void);
+
+/* ---------------------------------------------------------------- front end (HBM-bound) ------ */
+
+/* Log-mel features of n_streams clips (faster-whisper FeatureExtractor.__call__, padding=160).
+ *   audio_dev        fp32 concatenated 16 kHz samples
+ *   offsets_dev      int64 [n_streams+1] sample offsets into audio_dev
+ *   out_offsets_dev  int64 [n_streams]   element offsets into out_dev
+ *   tile_prefix_dev  int32 [n_streams+1] cumulative ceil(frames_s / 32), frames_s = N_s/160 + 1
+ *   out_dev          fp32; stream s gets a row-major [n_mels][frames_s] matrix
+ *   stream_max_dev   int32 [n_streams] scratch (per-call running max)
+ *   max_frames       max_s frames_s            n_mels 80 or 128 */
+int b200w_logmel(const float* audio_dev, const int64_t* offsets_dev, const int64_t* out_offsets_dev,
+                 const int32_t* tile_prefix_dev, int n_streams, int total_tiles, int n_mels,
+                 float* out_dev, int32_t* stream_max_dev, int max_frames, void* stream);
+
+/* Cut encoder windows out of log-mel features: window w = features of stream win_stream[w],
+ * frames [seeks[w], seeks[w]+3000), zero-padded (pad_or_trim on the FEATURES), transposed to
+ * time-major bf16 [n_windows][3000][128] (channels >= n_mels are zero). */
+int b200w_pack_windows(const float* feats_dev, const int64_t* feat_offsets_dev,
+                       const int32_t* n_frames_dev, const int32_t* seeks_dev,
+                       const int32_t* win_stream_dev, int n_windows, int n_mels,
+                       void* windows_bf16_dev, void* stream);
+
+/* AudioDeduplicator._extract_features for n_chunks chunks of the same audio buffer:
+ * [rms, centroid, zcr, rolloff85, bandwidth] / max|.|  -> out_dev fp32 [n_chunks][5];
+ * raw_out_dev (optional, may be NULL) receives the un-normalised values.
+ * max_points = max over chunks of (N even ? N/2 : N); must be <= 27648.  A chunk whose length has a
+ * prime factor > 64 is reported as NaN features. */
+int b200w_dedup_features(const float* audio_dev, const int64_t* offsets_dev, int n_chunks,
+                         int max_points, int sample_rate, float* out_dev, float* raw_out_dev,
+                         void* stream);
+
+/* ---------------------------------------------------------------- building blocks (tests) ---- */
+
+/* out[M][N] = act(A[M][K] * W[N][K]^T + bias) + residual.  bf16 operands, fp32 accumulate on
+ * tcgen05.  flags: bit0 out fp32, bit1 residual fp32, bit2 GELU.  force_bn: 0 | 64 | 128 | 256. */
+int b200w_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev,
+                    const void* residual_dev, void* out_dev, int M, int N, int K, int64_t lda,
+                    int64_t ldw, int64_t ldr, int64_t ldo, int flags, int force_bn, void* stream);
+
+/* conv1d (kernel 3, padding 1, stride 1 or 2) as implicit GEMM over time-major activations:
+ * x bf16 [B][T][C] -> GELU(conv(x) + bias) (+ addend fp32 [T_out][N], e.g. positions) ->
+ * out [B][T_out][N] bf16 or fp32.  w bf16 [N][3*C] tap-major.  C % 64 == 0. */
+int b200w_conv1d_k3(const void* x_dev, const void* w_dev, const float* bias_dev,
+                    const float* addend_dev, void* out_dev, int B, int T, int C, int N, int stride,
+                    int out_fp32, void* stream);
+
+/* Encoder self-attention: qkv bf16 [B][T][3d] -> out bf16 [B][T][d], heads of 64. */
+int b200w_enc_attention(const void* qkv_dev, int B, int T, int d, int n_heads, void* out_dev,
+                        void* stream);
+
+/* ---------------------------------------------------------------- engine --------------------- */
+
+typedef struct b200w_engine b200w_engine;
+
+typedef struct b200w_model_config {
+  int32_t n_mels;        /* 80 | 128 */
+  int32_t d_model;       /* 384 .. 1280, multiple of 64 */
+  int32_t n_heads;       /* d_model / 64 */
+  int32_t n_enc_layers;
+  int32_t n_dec_layers;
+  int32_t n_vocab;       /* 51865 | 51866 */
+  int32_t n_audio_ctx;   /* 1500 */
+  int32_t n_text_ctx;    /* 448 */
+  int32_t max_batch;     /* windows per encode / streams per decode */
+  int32_t max_beam;      /* >= 1 */
+} b200w_model_config;
+
+int b200w_engine_create(const b200w_model_config* cfg, b200w_engine** out);
+int b200w_engine_destroy(b200w_engine* e);
+
+/* Register one weight tensor (device memory owned by the caller, kept alive for the engine's
+ * lifetime).  dtype: 0 = fp32, 1 = bf16.  Names: see realtime-whisper-asr_b200/weights.py. */
+int b200w_engine_set_weight(b200w_engine* e, const char* name, const void* dev_ptr, int64_t numel,
+                            int dtype);
+/* All weights registered: validate and allocate workspaces. */
+int b200w_engine_finalize(b200w_engine* e);
+
+/* Whisper encoder on B windows: bf16 [B][3000][128] -> bf16 [B][1500][d]. */
+int b200w_encode(b200w_engine* e, const void* windows_dev, int B, void* enc_out_dev, void* stream);
+
+/* Cross-attention K/V of every decoder layer, once per chunk (one GEMM over all layers):
+ * enc_out bf16 [B][1500][d] -> cross_kv bf16 [B][1500][n_dec_layers][2][d]. */
+int b200w_cross_kv(b200w_engine* e, const void* enc_out_dev, int B, void* cross_kv_dev, void* stream);
+
+typedef struct b200w_decode_opts {
+  int32_t beam_size;             /* 1 = greedy */
+  float patience;                /* 1.0 */
+  float length_penalty;          /* 1.0 */
+  int32_t max_new_tokens;        /* cap on sampled tokens (<= n_text_ctx - prompt) ; 0 = no cap */
+  int32_t suppress_blank;        /* 1 */
+  int32_t without_timestamps;    /* 0 */
+  int32_t max_initial_timestamp_index; /* 50 */
+  int32_t eot, sot, no_speech, no_timestamps, timestamp_begin; /* token ids */
+  const int32_t* suppress_ids;   /* host, static suppress list */
+  int32_t n_suppress;
+  const int32_t* blank_ids;      /* host, tokens suppressed at the first sampled position */
+  int32_t n_blank;
+} b200w_decode_opts;
+
+/* Autoregressive decode of B chunks (greedy or beam search with Whisper's logit rules).
+ *   prompts_host      int32 concatenated prompt tokens, prompt_lens_host int32 [B]
+ *   tokens_out_host   int32 [B][max_out]   sampled tokens (without the prompt, without EOT)
+ *   n_tokens_out_host int32 [B]
+ *   sum_logprob_out_host fp32 [B]  cumulative log-prob of the returned hypothesis (incl. EOT)
+ *   no_speech_out_host   fp32 [B]  softmax prob of <|nospeech|> at the <|startoftranscript|> slot */
+int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t* prompts_host,
+                 const int32_t* prompt_lens_host, const b200w_decode_opts* opts,
+                 int32_t* tokens_out_host, int32_t max_out, int32_t* n_tokens_out_host,
+                 float* sum_logprob_out_host, float* no_speech_out_host, void* stream);
+
+/* Teacher-forced pass for word timing (CTranslate2 Whisper.align): for each of B sequences
+ * (tokens = sot_sequence + [no_timestamps] + text + [eot]) returns the DTW path between text
+ * tokens and encoder frames plus per-token probabilities.
+ *   align_heads_host  int32 [n_align][2] (layer, head)
+ *   num_frames_host   int32 [B]   content frames of the chunk (mel frames; //2 = encoder frames)
+ *   sot_len           tokens before the first text token (sot sequence + no_timestamps)
+ *   path_out_host     int32 [B][max_path][2] (text index, time index), path_len_out_host [B]
+ *   tok_prob_out_host fp32 [B][max_tok]  probability of each text token (teacher forced) */
+int b200w_align(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t* tokens_host,
+                const int32_t* token_lens_host, const int32_t* num_frames_host, int32_t sot_len,
+                const int32_t* align_heads_host, int32_t n_align, int32_t median_width,
+                int32_t* path_out_host, int32_t max_path, int32_t* path_len_out_host,
+                float* tok_prob_out_host, int32_t max_tok, void* stream);
+
+/* Language detection (faster-whisper detect_language): one decoder step on <|sot|>, softmax over
+ * the language tokens.  probs_out_host fp32 [B][n_lang]. */
+int b200w_detect_language(b200w_engine* e, const void* cross_kv_dev, int B, int32_t sot,
+                          const int32_t* lang_ids_host, int32_t n_lang, float* probs_out_host,
+                          void* stream);
+
+/* Debug / parity hooks: full-vocabulary logits of one teacher-forced pass.
+ * tokens_host concatenated, lens [B]; logits_out_dev fp32 [sum(lens)][n_vocab_padded]
+ * (n_vocab_padded = n_vocab rounded up to 8). */
+int b200w_decoder_logits(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t* tokens_host,
+                         const int32_t* token_lens_host, float* logits_out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200W_H_ */

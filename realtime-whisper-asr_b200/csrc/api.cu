@@ -1,0 +1,115 @@
+// extern "C" surface of libb200whisper.so: front end + building blocks.  (Engine entry points
+// live in engine.cu.)  Declarations: include/b200w.h.
+#include "../../include/b200w.h"
+
+#include "attention.h"
+#include "common.h"
+#include "frontend.h"
+#include "gemm.h"
+
+namespace b200w {
+
+unsigned long long g_launch_count = 0;
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& s) { t_last_error = s; }
+const char* get_last_error() { return t_last_error.c_str(); }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    B200W_CHECK_CUDA(cudaGetDevice(&dev));
+    B200W_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+}  // namespace b200w
+
+using namespace b200w;
+
+extern "C" {
+
+const char* b200w_last_error(void) { return get_last_error(); }
+int b200w_abi_version(void) { return B200W_ABI_VERSION; }
+uint64_t b200w_launch_count(void) { return g_launch_count; }
+
+int b200w_logmel(const float* audio_dev, const int64_t* offsets_dev, const int64_t* out_offsets_dev,
+                 const int32_t* tile_prefix_dev, int n_streams, int total_tiles, int n_mels,
+                 float* out_dev, int32_t* stream_max_dev, int max_frames, void* stream) {
+  B200W_API_BEGIN
+  logmel_launch(audio_dev, reinterpret_cast<const long long*>(offsets_dev),
+                reinterpret_cast<const long long*>(out_offsets_dev), tile_prefix_dev, n_streams,
+                total_tiles, n_mels, out_dev, stream_max_dev, max_frames,
+                static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
+int b200w_pack_windows(const float* feats_dev, const int64_t* feat_offsets_dev,
+                       const int32_t* n_frames_dev, const int32_t* seeks_dev,
+                       const int32_t* win_stream_dev, int n_windows, int n_mels,
+                       void* windows_bf16_dev, void* stream) {
+  B200W_API_BEGIN
+  pack_windows_launch(feats_dev, reinterpret_cast<const long long*>(feat_offsets_dev), n_frames_dev,
+                      seeks_dev, win_stream_dev, n_windows, n_mels,
+                      static_cast<bf16*>(windows_bf16_dev), static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
+int b200w_dedup_features(const float* audio_dev, const int64_t* offsets_dev, int n_chunks,
+                         int max_points, int sample_rate, float* out_dev, float* raw_out_dev,
+                         void* stream) {
+  B200W_API_BEGIN
+  dedup_features_launch(audio_dev, reinterpret_cast<const long long*>(offsets_dev), n_chunks,
+                        max_points, sample_rate, out_dev, raw_out_dev,
+                        static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
+int b200w_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev,
+                    const void* residual_dev, void* out_dev, int M, int N, int K, int64_t lda,
+                    int64_t ldw, int64_t ldr, int64_t ldo, int flags, int force_bn, void* stream) {
+  B200W_API_BEGIN
+  GemmDesc d;
+  d.A = static_cast<const bf16*>(A_dev);
+  d.a_rows = M;
+  d.a_cols = K;
+  d.batches = 1;
+  d.a_row_stride = lda;
+  d.W = static_cast<const bf16*>(W_dev);
+  d.N = N;
+  d.K = K;
+  d.w_row_stride = ldw;
+  d.out_rows = M;
+  d.bias = bias_dev;
+  d.act = (flags & 4) ? 1 : 0;
+  d.residual = residual_dev;
+  d.res_fp32 = (flags & 2) ? 1 : 0;
+  d.res_row_stride = ldr;
+  d.out = out_dev;
+  d.out_fp32 = (flags & 1) ? 1 : 0;
+  d.out_row_stride = ldo;
+  d.force_bn = force_bn;
+  gemm_bf16(d, static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
+int b200w_conv1d_k3(const void* x_dev, const void* w_dev, const float* bias_dev,
+                    const float* addend_dev, void* out_dev, int B, int T, int C, int N, int stride,
+                    int out_fp32, void* stream) {
+  B200W_API_BEGIN
+  conv1d_k3(static_cast<const bf16*>(x_dev), static_cast<const bf16*>(w_dev), bias_dev, addend_dev,
+            out_dev, B, T, C, N, stride, out_fp32, static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
+int b200w_enc_attention(const void* qkv_dev, int B, int T, int d, int n_heads, void* out_dev,
+                        void* stream) {
+  B200W_API_BEGIN
+  enc_attention(static_cast<const bf16*>(qkv_dev), B, T, d, n_heads, static_cast<bf16*>(out_dev),
+                static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,325 @@
+// Attention kernels.
+//  * enc_attn_kernel: non-causal flash-style self-attention for the encoder (T = 1500, head 64).
+//    S = Q K^T and O += P V run on tcgen05 with fp32 accumulators in TMEM; Q/K/V tiles arrive by
+//    TMA (128B swizzle) straight out of the fused QKV activation; the online softmax runs in
+//    registers (one query row per thread, exp2 domain) and hands P back through shared memory.
+//    Two CTAs per SM overlap each other's MMA and softmax phases.
+//  * dec_attn_kernel: decoder attention for few queries (decode steps, prompt prefill, the
+//    alignment pass): one warp per (query, head), keys/values gathered through the token-granular
+//    page table of the KV cache (self) or read densely from the per-chunk cross K/V.  Memory-bound
+//    CUDA-core work.  Optionally exports softmax probabilities of selected heads (alignment).
+#include "attention.h"
+
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace b200w {
+
+static constexpr int QT = 128;   // queries per CTA
+static constexpr int KT = 128;   // keys per inner block
+static constexpr int HD = 64;    // head dim
+static constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB
+
+struct EncAttnParams {
+  int T, d;
+  float scale_log2e;
+  bf16* out;  // [B][T][d]
+};
+
+__global__ void __launch_bounds__(128, 2)
+enc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const EncAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;
+  uint8_t* sV = smem + 2 * TILE_BYTES;
+  uint8_t* sP = smem + 3 * TILE_BYTES;  // two 16 KB halves: keys 0..63 | 64..127
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
+  const uint32_t barQ = smem_u32(bars), barK = smem_u32(bars + 1), barV = smem_u32(bars + 2),
+                 barS = smem_u32(bars + 3), barO = smem_u32(bars + 4);
+
+  if (tid == 0) {
+    mbar_init(barQ, 1);
+    mbar_init(barK, 1);
+    mbar_init(barV, 1);
+    mbar_init(barS, 1);
+    mbar_init(barO, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQKV);
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+
+  const int nblk = (p.T + KT - 1) / KT;
+  const int colQ = h * HD, colK = p.d + h * HD, colV = 2 * p.d + h * HD;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(barQ, TILE_BYTES);
+    tma_load_3d(smem_u32(sQ), &tmQKV, barQ, colQ, q0, b);
+    mbar_arrive_expect_tx(barK, TILE_BYTES);
+    tma_load_3d(smem_u32(sK), &tmQKV, barK, colK, 0, b);
+    mbar_arrive_expect_tx(barV, TILE_BYTES);
+    tma_load_3d(smem_u32(sV), &tmQKV, barV, colV, 0, b);
+  }
+
+  constexpr uint32_t idescS = make_idesc_bf16(128, 128, 0, 0);  // Q (K-major) x K (K-major)
+  constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major)
+
+  float o[HD];
+#pragma unroll
+  for (int i = 0; i < HD; ++i) o[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  const int r = tid;  // query row inside the tile == TMEM lane
+
+  for (int j = 0; j < nblk; ++j) {
+    const uint32_t ph = j & 1;
+    if (tid == 0) {
+      if (j == 0) mbar_wait(barQ, 0);
+      mbar_wait(barK, ph);
+      tc_fence_after();
+      const uint64_t qd = make_sw128_desc(smem_u32(sQ));
+      const uint64_t kd = make_sw128_desc(smem_u32(sK));
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_S, qd + 2 * k, kd + 2 * k, idescS, k != 0);
+      tc_commit(barS);
+    }
+    mbar_wait(barS, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < nblk) {  // K tile is free again: prefetch the next one
+      mbar_arrive_expect_tx(barK, TILE_BYTES);
+      tma_load_3d(smem_u32(sK), &tmQKV, barK, colK, (j + 1) * KT, b);
+    }
+    const int kv_valid = min(KT, p.T - j * KT);
+    // pass 1: row max
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < KT; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_S + lane_sel + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+    }
+    const float m_new = fmaxf(m_run, mx * p.scale_log2e);
+    const float alpha = exp2f(m_run - m_new);  // first block: exp2(-inf) = 0
+    m_run = m_new;
+    float lsum = 0.f;
+    // pass 2: p = exp2(s * scale - m), bf16, into the swizzled K-major P tile
+#pragma unroll 1
+    for (int c0 = 0; c0 < KT; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_S + lane_sel + c0, v);
+      tmem_ld_wait();
+      uint32_t packed[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = c0 + i < kv_valid ? exp2f(__uint_as_float(v[i]) * p.scale_log2e - m_new) : 0.f;
+        float p1 = c0 + i + 1 < kv_valid ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2e - m_new) : 0.f;
+        __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+        // the PV product sees bf16 P: sum exactly what it sees so rows stay normalised
+        lsum += __bfloat162float(pb.x) + __bfloat162float(pb.y);
+        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+      }
+      uint8_t* half = sP + (c0 >> 6) * TILE_BYTES + r * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {  // four 16-byte chunks (8 keys each)
+        const int chunk = ((c0 & 63) >> 3) + cc;
+        *reinterpret_cast<uint4*>(half + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(packed[4 * cc], packed[4 * cc + 1], packed[4 * cc + 2], packed[4 * cc + 3]);
+      }
+    }
+    l_run = l_run * alpha + lsum;
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] *= alpha;
+    fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the MMA's async proxy
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(barV, ph);
+      tc_fence_after();
+      const uint64_t vd = make_sw128_desc(smem_u32(sV));
+#pragma unroll
+      for (int k = 0; k < KT / 16; ++k) {
+        const uint64_t pd = make_sw128_desc(smem_u32(sP + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
+        tc_mma_bf16(tmem_O, pd, vd + 128 * k, idescO, k != 0);  // V: +16 key rows = +2048 B
+      }
+      tc_commit(barO);
+    }
+    mbar_wait(barO, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < nblk) {
+      mbar_arrive_expect_tx(barV, TILE_BYTES);
+      tma_load_3d(smem_u32(sV), &tmQKV, barV, colV, (j + 1) * KT, b);
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_O + lane_sel + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c0 + i] += __uint_as_float(v[i]);
+    }
+    tc_fence_before();  // next iteration's MMAs overwrite S / O after the CTA-wide sync below
+    __syncthreads();
+  }
+
+  const int t = q0 + r;
+  if (t < p.T) {
+    const float inv = 1.0f / l_run;
+    bf16* dst = p.out + ((long long)b * p.T + t) * p.d + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) {
+      uint4 u;
+      __nv_bfloat162* u2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) u2[i] = __floats2bfloat162_rn(o[c + 2 * i] * inv, o[c + 2 * i + 1] * inv);
+      *reinterpret_cast<uint4*>(dst + c) = u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+void enc_attention(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out, cudaStream_t stream) {
+  B200W_REQUIRE(d == n_heads * HD, "head dim must be 64");
+  if (B <= 0) return;
+  CUtensorMap tm;
+  make_tmap_bf16_3d(&tm, qkv, 3 * (uint64_t)d, T, B, 3 * (uint64_t)d, (uint64_t)T * 3 * d, HD, 128);
+  constexpr int smem_bytes = 5 * TILE_BYTES + 5 * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200W_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          smem_bytes));
+    configured = true;
+  }
+  EncAttnParams p{T, d, 0.125f * 1.4426950408889634f, out};
+  enc_attn_kernel<<<dim3(cdiv(T, QT), n_heads, B), 128, smem_bytes, stream>>>(tm, p);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------ decoder attention
+static constexpr int DEC_WARPS = 2;
+
+__global__ void __launch_bounds__(DEC_WARPS * 32) dec_attn_kernel(const DecAttnParams p) {
+  extern __shared__ float s_scores[];  // [DEC_WARPS][max_len]
+  const int qi = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y * DEC_WARPS + warp;
+  float* sc = s_scores + warp * p.max_len;
+  const int len = p.kvlen[qi];
+  const int tr = p.trow[qi];
+  const int* tab = p.table ? p.table + (long long)tr * p.table_stride : nullptr;
+  const long long base = p.kv_base_off ? p.kv_base_off[tr] : 0;
+  const bf16* kb = p.kbase + base + h * HD;
+  const bf16* vb = p.vbase + base + h * HD;
+
+  // q in registers (every lane holds the whole 64-vector, pre-scaled)
+  float q[HD];
+  {
+    const bf16* qp = p.q + (long long)qi * p.q_stride + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(qp + c);
+      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(u2[i]);
+        q[c + 2 * i] = f.x * p.scale;
+        q[c + 2 * i + 1] = f.y * p.scale;
+      }
+    }
+  }
+  float mx = -INFINITY;
+  for (int i = lane; i < len; i += 32) {
+    const long long slot = tab ? tab[i] : i;
+    const bf16* kp = kb + slot * p.kv_row_stride;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(kp + c));
+      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(u2[t]);
+        acc = fmaf(q[c + 2 * t], f.x, acc);
+        acc = fmaf(q[c + 2 * t + 1], f.y, acc);
+      }
+    }
+    sc[i] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int i = lane; i < len; i += 32) {
+    const float e = __expf(sc[i] - mx);
+    sc[i] = e;
+    sum += e;
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  __syncwarp();
+
+  const int ex = p.head_export ? p.head_export[h] : -1;
+  if (ex >= 0) {
+    float* dst = p.probs_out + ((long long)ex * p.n_queries + qi) * p.probs_stride;
+    for (int i = lane; i < len; i += 32) dst[i] = sc[i] * inv;
+  }
+
+  float2 acc = make_float2(0.f, 0.f);
+  const bf16* vl = vb + 2 * lane;
+  int i = 0;
+  for (; i + 4 <= len; i += 4) {  // 4 independent 128-byte row reads in flight per warp
+    long long s0, s1, s2, s3;
+    if (tab) { s0 = tab[i]; s1 = tab[i + 1]; s2 = tab[i + 2]; s3 = tab[i + 3]; }
+    else { s0 = i; s1 = i + 1; s2 = i + 2; s3 = i + 3; }
+    const __nv_bfloat162 v0 = *reinterpret_cast<const __nv_bfloat162*>(vl + s0 * p.kv_row_stride);
+    const __nv_bfloat162 v1 = *reinterpret_cast<const __nv_bfloat162*>(vl + s1 * p.kv_row_stride);
+    const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(vl + s2 * p.kv_row_stride);
+    const __nv_bfloat162 v3 = *reinterpret_cast<const __nv_bfloat162*>(vl + s3 * p.kv_row_stride);
+    const float p0 = sc[i], p1 = sc[i + 1], p2 = sc[i + 2], p3 = sc[i + 3];
+    float2 f;
+    f = __bfloat1622float2(v0); acc.x = fmaf(p0, f.x, acc.x); acc.y = fmaf(p0, f.y, acc.y);
+    f = __bfloat1622float2(v1); acc.x = fmaf(p1, f.x, acc.x); acc.y = fmaf(p1, f.y, acc.y);
+    f = __bfloat1622float2(v2); acc.x = fmaf(p2, f.x, acc.x); acc.y = fmaf(p2, f.y, acc.y);
+    f = __bfloat1622float2(v3); acc.x = fmaf(p3, f.x, acc.x); acc.y = fmaf(p3, f.y, acc.y);
+  }
+  for (; i < len; ++i) {
+    const long long s0 = tab ? tab[i] : i;
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vl + s0 * p.kv_row_stride));
+    acc.x = fmaf(sc[i], f.x, acc.x);
+    acc.y = fmaf(sc[i], f.y, acc.y);
+  }
+  bf16* op = p.out + (long long)qi * p.out_stride + h * HD + 2 * lane;
+  *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
+}
+
+void dec_attention(const DecAttnParams& p, int n_heads, cudaStream_t stream) {
+  if (p.n_queries <= 0) return;
+  B200W_REQUIRE(n_heads % DEC_WARPS == 0, "head count must be even");
+  const size_t smem = (size_t)DEC_WARPS * p.max_len * sizeof(float);
+  dec_attn_kernel<<<dim3(p.n_queries, n_heads / DEC_WARPS), DEC_WARPS * 32, smem, stream>>>(p);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+}  // namespace b200w

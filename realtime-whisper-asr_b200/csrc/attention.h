@@ -1,0 +1,34 @@
+// Attention launchers (attention.cu).  All pointers are device pointers.
+#pragma once
+#include "common.h"
+
+namespace b200w {
+
+// Encoder self-attention over the fused QKV activation: qkv bf16 [B][T][3d] (q | k | v, heads of
+// 64 inside each third) -> out bf16 [B][T][d].  softmax(q k^T / 8) v, non-causal.
+void enc_attention(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out, cudaStream_t stream);
+
+// Decoder attention for a handful of queries; one warp per (query, head).
+struct DecAttnParams {
+  const bf16* q = nullptr;   // query i, head h at q + i * q_stride + h * 64
+  int q_stride = 0;
+  const bf16* kbase = nullptr;  // key of slot s, head h at kbase + base_off + s * kv_row_stride + h * 64
+  const bf16* vbase = nullptr;
+  long long kv_row_stride = 0;
+  const int* table = nullptr;   // [rows][table_stride] position -> slot; null = identity
+  int table_stride = 0;
+  const int* trow = nullptr;    // [n_queries] table row (self) / stream index (cross)
+  const long long* kv_base_off = nullptr;  // [rows] element offset per table row / stream, or null
+  const int* kvlen = nullptr;   // [n_queries] number of visible keys
+  bf16* out = nullptr;          // [n_queries][out_stride]
+  int out_stride = 0;
+  float scale = 0.125f;
+  int n_queries = 0;
+  int max_len = 0;              // upper bound on kvlen (sizes the score scratch)
+  float* probs_out = nullptr;   // optional [n_export][n_queries][probs_stride]
+  const int* head_export = nullptr;  // [n_heads] -> export index or -1
+  int probs_stride = 0;
+};
+void dec_attention(const DecAttnParams& p, int n_heads, cudaStream_t stream);
+
+}  // namespace b200w

@@ -1,0 +1,23 @@
+// Launchers for the HBM-bound front-end kernels (frontend.cu).  All pointers are device pointers.
+#pragma once
+#include "common.h"
+
+namespace b200w {
+
+// log-mel of n_streams concatenated clips.  out holds, per stream s, a [n_mels][N_s/160 + 1] fp32
+// matrix at element offset out_offsets[s].  tile_prefix[s] = sum_{j<s} ceil(frames_j / 32).
+void logmel_launch(const float* audio, const long long* offsets, const long long* out_offsets,
+                   const int* tile_prefix, int n_streams, int total_tiles, int n_mels, float* out,
+                   int* stream_max, int max_frames, cudaStream_t stream);
+
+// Cut 3000-frame encoder windows (bf16, time-major, 128 channels) out of the fp32 features.
+void pack_windows_launch(const float* feats, const long long* feat_offsets, const int* n_frames,
+                         const int* seeks, const int* win_stream, int n_windows, int n_mels,
+                         bf16* windows, cudaStream_t stream);
+
+// Audio-dedup features, one CTA per chunk.  out / raw_out: [n_chunks][5].
+void dedup_features_launch(const float* audio, const long long* offsets, int n_chunks,
+                           int max_points, int sample_rate, float* out, float* raw_out,
+                           cudaStream_t stream);
+
+}  // namespace b200w

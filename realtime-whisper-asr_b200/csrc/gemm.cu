@@ -1,0 +1,398 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:
+//   TMA (128B-swizzled tiles) -> shared memory ring -> tcgen05.mma (fp32 accumulators in TMEM,
+//   double-buffered) -> tcgen05.ld epilogue (bias / GELU / residual / bf16|fp32 store).
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+// The A operand may be addressed through up to three "taps" (row shift + column offset), which
+// turns the same kernel into an implicit-GEMM conv1d over time-major activations; TMA zero-fills
+// the out-of-range rows that the conv padding needs.
+#include "gemm.h"
+
+#include <mutex>
+
+#include "ptx.cuh"
+
+namespace b200w {
+
+static constexpr int BM = 128, BK = 64;
+static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+
+struct GemmParams {
+  int out_rows, batches, N;
+  int m_tiles_per_batch, n_tiles, total_tiles;
+  int n_taps;
+  int tap_shift[3], tap_col[3], tap_kb[3];
+  int total_kb;
+  const float* bias;
+  int act;
+  const void* residual;
+  int res_fp32;
+  long long res_rs, res_bs;
+  void* out;
+  int out_fp32;
+  long long out_rs, out_bs;
+};
+
+// 32 accumulator columns of one output row -> global memory.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int b,
+                                               int r, int n) {
+  const long long out_off = (long long)b * p.out_bs + (long long)r * p.out_rs;
+  const long long res_off = (long long)b * p.res_bs + (long long)r * p.res_rs;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int ng = n + 8 * g;
+    if (ng >= p.N) break;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[8 * g + j]);
+    if (ng + 8 <= p.N) {
+      if (p.bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ng));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ng + 4));
+        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+        x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+      }
+      if (p.residual) {
+        if (p.res_fp32) {
+          const float* rp = reinterpret_cast<const float*>(p.residual) + res_off + ng;
+          const float4 r0 = *reinterpret_cast<const float4*>(rp);
+          const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+          x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+          x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+        } else {
+          const uint4 rr = *reinterpret_cast<const uint4*>(
+              reinterpret_cast<const bf16*>(p.residual) + res_off + ng);
+          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(r2[j]);
+            x[2 * j] += f.x;
+            x[2 * j + 1] += f.y;
+          }
+        }
+      }
+      if (p.out_fp32) {
+        float* op = reinterpret_cast<float*>(p.out) + out_off + ng;
+        *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
+      } else {
+        uint4 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_off + ng) = o;
+      }
+    } else {  // ragged N tail: scalar
+      for (int j = 0; j < 8 && ng + j < p.N; ++j) {
+        float y = x[j];
+        if (p.bias) y += __ldg(p.bias + ng + j);
+        if (p.act == 1) y = gelu_erf(y);
+        if (p.residual) {
+          y += p.res_fp32 ? reinterpret_cast<const float*>(p.residual)[res_off + ng + j]
+                          : __bfloat162float(
+                                reinterpret_cast<const bf16*>(p.residual)[res_off + ng + j]);
+        }
+        if (p.out_fp32)
+          reinterpret_cast<float*>(p.out)[out_off + ng + j] = y;
+        else
+          reinterpret_cast<bf16*>(p.out)[out_off + ng + j] = __float2bfloat16(y);
+      }
+    }
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(bars);
+  const uint32_t empty0 = smem_u32(bars + STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES);
+  const uint32_t tempty0 = smem_u32(bars + 2 * STAGES + 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int b = mt / p.m_tiles_per_batch;
+        const int r0 = (mt % p.m_tiles_per_batch) * BM;
+        const int n0 = nt * BN;
+        int kbg = 0;
+        for (int t = 0; t < p.n_taps; ++t) {
+          for (int kb = 0; kb < p.tap_kb[t]; ++kb, ++kbg) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_arrive_expect_tx(fb, A_BYTES + B_BYTES);
+            tma_load_3d(smem_u32(sA + stage * A_BYTES), &tmA, fb, p.tap_col[t] + kb * BK,
+                        r0 + p.tap_shift[t], b);
+            tma_load_3d(smem_u32(sB + stage * B_BYTES), &tmB, fb, kbg * BK, n0, 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.total_kb; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t ad = make_sw128_desc(smem_u32(sA + stage * A_BYTES));
+          const uint64_t bd = make_sw128_desc(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K step inside the swizzle row
+            tc_mma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {  // ---------------- epilogue warps 2..5 (TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int b = mt / p.m_tiles_per_batch;
+      const int r = (mt % p.m_tiles_per_batch) * BM + q * 32 + lane;
+      const int n0 = nt * BN;
+      const bool row_ok = r < p.out_rows;
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 == BN) {  // accumulator drained: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty0 + 8 * acc);
+        }
+        if (row_ok && n0 + c0 < p.N) epilogue_chunk(p, v, b, r, n0 + c0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  if (!fn) throw Error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+  return fn;
+}
+
+void make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+  B200W_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  B200W_REQUIRE((stride1_elems * 2) % 16 == 0 && (stride2_elems * 2) % 16 == 0,
+                "TMA strides must be multiples of 16 bytes");
+  B200W_REQUIRE(box0 * 2 == 128 && box1 <= 256, "box must be 64 bf16 wide and at most 256 rows");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base),
+                               dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (%d) dims=[%llu,%llu,%llu] strides=[%llu,%llu] box=[%u,%u]",
+             (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+             (unsigned long long)strides[0], (unsigned long long)strides[1], box0, box1);
+    throw Error(buf);
+  }
+}
+
+template <int BN, int STAGES>
+static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p,
+                        cudaStream_t stream) {
+  constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200W_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  p.n_tiles = cdiv(p.N, BN);
+  p.total_tiles = p.n_tiles * p.m_tiles_per_batch * p.batches;
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  gemm_tcgen05_kernel<BN, STAGES><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
+  B200W_REQUIRE(d.A && d.W && d.out, "null operand");
+  B200W_REQUIRE(d.K % BK == 0 && d.K > 0, "K must be a positive multiple of 64");
+  B200W_REQUIRE(d.out_row_stride % 8 == 0, "output row stride must be a multiple of 8 elements");
+  B200W_REQUIRE((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "output must be 16-byte aligned");
+  B200W_REQUIRE(!d.bias || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "bias must be 16-byte aligned");
+  B200W_REQUIRE(!d.residual || ((reinterpret_cast<uintptr_t>(d.residual) & 15) == 0 &&
+                                d.res_row_stride % 8 == 0),
+                "residual must be 16-byte aligned with row stride % 8 == 0");
+  if (d.out_rows <= 0 || d.batches <= 0 || d.N <= 0) return;
+
+  GemmParams p{};
+  p.out_rows = d.out_rows;
+  p.batches = d.batches;
+  p.N = d.N;
+  p.m_tiles_per_batch = cdiv(d.out_rows, BM);
+  if (d.n_taps == 0) {
+    p.n_taps = 1;
+    p.tap_shift[0] = 0;
+    p.tap_col[0] = 0;
+    p.tap_kb[0] = d.K / BK;
+  } else {
+    B200W_REQUIRE(d.n_taps <= 3, "at most 3 taps");
+    p.n_taps = d.n_taps;
+    for (int t = 0; t < d.n_taps; ++t) {
+      p.tap_shift[t] = d.taps[t].row_shift;
+      p.tap_col[t] = d.taps[t].col_off;
+      p.tap_kb[t] = d.taps[t].kblocks;
+    }
+  }
+  p.total_kb = 0;
+  for (int t = 0; t < p.n_taps; ++t) p.total_kb += p.tap_kb[t];
+  B200W_REQUIRE(p.total_kb * BK == d.K, "taps must cover K exactly");
+  p.bias = d.bias;
+  p.act = d.act;
+  p.residual = d.residual;
+  p.res_fp32 = d.res_fp32;
+  p.res_rs = d.res_row_stride;
+  p.res_bs = d.res_batch_stride;
+  p.out = d.out;
+  p.out_fp32 = d.out_fp32;
+  p.out_rs = d.out_row_stride;
+  p.out_bs = d.out_batch_stride;
+
+  // Tile width: widest tile that still gives every SM work; narrow tiles for skinny (decode) GEMMs.
+  int bn = d.force_bn;
+  if (bn == 0) {
+    const long long mt = (long long)p.m_tiles_per_batch * p.batches;
+    if (d.N % 256 == 0 && mt * (d.N / 256) >= 2LL * num_sms()) bn = 256;
+    else if (mt * cdiv(d.N, 128) >= num_sms()) bn = 128;
+    else bn = 64;
+  }
+  CUtensorMap tmA, tmB;
+  const uint64_t a_bs = d.batches > 1 ? (uint64_t)d.a_batch_stride
+                                      : (uint64_t)d.a_rows * (uint64_t)d.a_row_stride;
+  make_tmap_bf16_3d(&tmA, d.A, d.a_cols, d.a_rows, d.batches, d.a_row_stride, a_bs, BK, BM);
+  make_tmap_bf16_3d(&tmB, d.W, d.K, d.N, 1, d.w_row_stride, (uint64_t)d.N * d.w_row_stride, BK, bn);
+  if (bn == 256) launch_gemm<256, 4>(tmA, tmB, p, stream);
+  else if (bn == 128) launch_gemm<128, 6>(tmA, tmB, p, stream);
+  else if (bn == 64) launch_gemm<64, 8>(tmA, tmB, p, stream);
+  else throw Error("force_bn must be 64, 128 or 256");
+}
+
+void conv1d_k3(const bf16* x, const bf16* w, const float* bias, const float* addend, void* out, int B,
+               int T, int C, int N, int stride, int out_fp32, cudaStream_t stream) {
+  B200W_REQUIRE(C % BK == 0, "conv channels must be a multiple of 64");
+  B200W_REQUIRE(stride == 1 || (stride == 2 && T % 2 == 0), "stride must be 1, or 2 with even T");
+  GemmDesc d;
+  d.W = w;
+  d.N = N;
+  d.K = 3 * C;
+  d.w_row_stride = 3 * C;
+  d.bias = bias;
+  d.act = 1;
+  d.residual = addend;
+  d.res_fp32 = 1;
+  d.res_row_stride = N;
+  d.res_batch_stride = 0;
+  d.out = out;
+  d.out_fp32 = out_fp32;
+  d.out_row_stride = N;
+  d.A = x;
+  d.batches = B;
+  d.a_batch_stride = (int64_t)T * C;
+  if (stride == 1) {
+    // taps read rows t-1, t, t+1; TMA zero-fills rows -1 and T (the conv padding)
+    d.a_rows = T;
+    d.a_cols = C;
+    d.a_row_stride = C;
+    d.out_rows = T;
+    d.n_taps = 3;
+    d.taps[0] = GemmTap{-1, 0, C / BK};
+    d.taps[1] = GemmTap{0, 0, C / BK};
+    d.taps[2] = GemmTap{1, 0, C / BK};
+  } else {
+    // view x as [T/2][2C] (row r = x[2r] | x[2r+1]): out[t] = W0 x[2t-1] + W1 x[2t] + W2 x[2t+1]
+    //   = W0 * row(t-1)[C:2C] + [W1 W2] * row(t)[0:2C]
+    d.a_rows = T / 2;
+    d.a_cols = 2 * C;
+    d.a_row_stride = 2 * C;
+    d.out_rows = T / 2;
+    d.n_taps = 2;
+    d.taps[0] = GemmTap{-1, C, C / BK};
+    d.taps[1] = GemmTap{0, 0, 2 * C / BK};
+  }
+  d.out_batch_stride = (int64_t)d.out_rows * N;
+  gemm_bf16(d, stream);
+}
+
+}  // namespace b200w

@@ -1,0 +1,126 @@
+"""Host side of the fused front end: log-mel features and audio-dedup features on the GPU.
+
+Replaces faster-whisper's ``FeatureExtractor.__call__`` (NumPy; reached from
+``/root/reference/asr_components.py:279-288``) and the arithmetic of
+``/root/reference/audio_deduplicator.py:60-181``.  PyTorch is used for device buffers only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+HOP = 160
+SAMPLE_RATE = 16000
+N_FRAMES = 3000
+TILE_FRAMES = 32
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.B200WError("CUDA device required: the B200 backend has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+@dataclass
+class MelBatch:
+    """Log-mel features of a batch of clips, resident on the device.
+
+    feats: flat fp32 tensor; clip s is ``feats[offsets[s]:offsets[s+1]].view(n_mels, n_frames[s])``.
+    """
+    feats: torch.Tensor
+    offsets: List[int]
+    n_frames: List[int]
+    n_mels: int
+    feat_offsets_dev: torch.Tensor
+    n_frames_dev: torch.Tensor
+
+    def clip(self, s: int) -> torch.Tensor:
+        return self.feats[self.offsets[s]: self.offsets[s + 1]].view(self.n_mels, self.n_frames[s])
+
+
+def upload_audio(audios: Sequence[np.ndarray], device) -> tuple[torch.Tensor, np.ndarray]:
+    """Concatenate clips into one pinned host buffer and copy it to the device (async)."""
+    lens = np.array([len(a) for a in audios], dtype=np.int64)
+    offsets = np.zeros(len(audios) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    total = int(offsets[-1])
+    host = torch.empty(max(total, 1), dtype=torch.float32, pin_memory=True)
+    hv = host.numpy()
+    for a, o in zip(audios, offsets[:-1]):
+        hv[o:o + len(a)] = np.asarray(a, dtype=np.float32)
+    return host.to(device, non_blocking=True), offsets
+
+
+def log_mel(audio_dev: torch.Tensor, offsets: np.ndarray, n_mels: int) -> MelBatch:
+    """Batched log-mel of clips already on the device (offsets: host int64 [n+1])."""
+    lib = _lib.load()
+    device = audio_dev.device
+    n = len(offsets) - 1
+    lens = np.diff(offsets)
+    n_frames = (lens // HOP + 1).astype(np.int64)
+    out_sizes = n_frames * n_mels
+    out_offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(out_sizes, out=out_offsets[1:])
+    tiles = (n_frames + TILE_FRAMES - 1) // TILE_FRAMES
+    tile_prefix = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(tiles, out=tile_prefix[1:])
+    # one small metadata upload: [offsets | out_offsets] int64, [tile_prefix | n_frames] int32
+    meta64 = torch.from_numpy(np.concatenate([offsets, out_offsets])).to(device, non_blocking=True)
+    meta32 = torch.from_numpy(np.concatenate([tile_prefix, n_frames.astype(np.int32)])).to(
+        device, non_blocking=True)
+    feats = torch.empty(int(out_offsets[-1]), dtype=torch.float32, device=device)
+    smax = torch.empty(n, dtype=torch.int32, device=device)
+    off_dev = meta64[: n + 1]
+    oo_dev = meta64[n + 1:]
+    tp_dev = meta32[: n + 1]
+    nf_dev = meta32[n + 1:]
+    _lib.check(lib.b200w_logmel(audio_dev.data_ptr(), off_dev.data_ptr(), oo_dev.data_ptr(),
+                                tp_dev.data_ptr(), n, int(tile_prefix[-1]), n_mels, feats.data_ptr(),
+                                smax.data_ptr(), int(n_frames.max()), _stream_ptr(device)))
+    return MelBatch(feats, [int(x) for x in out_offsets], [int(x) for x in n_frames], n_mels,
+                    oo_dev, nf_dev)
+
+
+def pack_windows(mel: MelBatch, win_stream: Sequence[int], seeks: Sequence[int]) -> torch.Tensor:
+    """Encoder input windows bf16 [n_windows, 3000, 128] (zero-padded features, time-major)."""
+    lib = _lib.load()
+    device = mel.feats.device
+    nw = len(win_stream)
+    meta = torch.tensor(list(seeks) + list(win_stream), dtype=torch.int32).to(device, non_blocking=True)
+    windows = torch.empty((nw, N_FRAMES, 128), dtype=torch.bfloat16, device=device)
+    _lib.check(lib.b200w_pack_windows(mel.feats.data_ptr(), mel.feat_offsets_dev.data_ptr(),
+                                      mel.n_frames_dev.data_ptr(), meta[:nw].data_ptr(),
+                                      meta[nw:].data_ptr(), nw, mel.n_mels, windows.data_ptr(),
+                                      _stream_ptr(device)))
+    return windows
+
+
+def dedup_features(audio_dev: torch.Tensor, offsets: np.ndarray, sample_rate: int = SAMPLE_RATE,
+                   return_raw: bool = False):
+    """AudioDeduplicator._extract_features for every chunk; returns fp32 [n_chunks, 5] on device."""
+    lib = _lib.load()
+    device = audio_dev.device
+    n = len(offsets) - 1
+    lens = np.diff(offsets)
+    if n == 0:
+        z = torch.zeros((0, 5), dtype=torch.float32, device=device)
+        return (z, z) if return_raw else z
+    pts = np.where(lens % 2 == 0, lens // 2, lens)
+    max_points = int(pts.max())
+    off_dev = torch.from_numpy(np.asarray(offsets, dtype=np.int64)).to(device, non_blocking=True)
+    out = torch.empty((n, 5), dtype=torch.float32, device=device)
+    raw = torch.empty((n, 5), dtype=torch.float32, device=device) if return_raw else None
+    _lib.check(lib.b200w_dedup_features(audio_dev.data_ptr(), off_dev.data_ptr(), n, max_points,
+                                        sample_rate, out.data_ptr(),
+                                        raw.data_ptr() if raw is not None else None,
+                                        _stream_ptr(device)))
+    return (out, raw) if return_raw else out

@@ -1,0 +1,99 @@
+"""GPU parity tests of the building blocks, through the C ABI (ctypes), vs plain torch fp32."""
+import numpy as np
+import pytest
+import torch
+
+from realtime_whisper_asr_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(lib, A, W, bias=None, res=None, out_fp32=False, gelu=False, force_bn=0):
+    M, K = A.shape
+    N = W.shape[0]
+    ldo = (N + 7) // 8 * 8
+    out = torch.zeros((M, ldo), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=A.device)
+    flags = (1 if out_fp32 else 0) | (2 if (res is not None and res.dtype == torch.float32) else 0) | (4 if gelu else 0)
+    _lib.check(lib.b200w_gemm_bf16(A.data_ptr(), W.data_ptr(),
+                                   bias.data_ptr() if bias is not None else None,
+                                   res.data_ptr() if res is not None else None, out.data_ptr(),
+                                   M, N, K, A.stride(0), W.stride(0),
+                                   res.stride(0) if res is not None else 0, ldo, flags, force_bn,
+                                   torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return out[:, :N]
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 64, 128), (128, 256, 128, 256), (128, 64, 64, 64),
+    (300, 384, 384, 0), (1500, 1280, 1280, 0), (1500, 3840, 1280, 256), (777, 1000, 512, 128),
+    (5, 1280, 1280, 0), (160, 5120, 1280, 64), (33, 51866, 384, 0), (3000, 384, 1536, 0),
+])
+def test_gemm_plain(lib, cuda_device, M, N, K, bn):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(cuda_device)
+    out = _gemm(lib, A, W, out_fp32=True, force_bn=bn)
+    ref = A.float() @ W.float().T
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+def test_gemm_epilogues(lib, cuda_device):
+    g = torch.Generator(device="cpu").manual_seed(5)
+    M, N, K = 515, 768, 256
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    W = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16).to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    res32 = torch.randn(M, N, generator=g).to(cuda_device)
+    res16 = res32.to(torch.bfloat16)
+    base = A.float() @ W.float().T + bias
+    # bias + GELU -> bf16
+    out = _gemm(lib, A, W, bias=bias, gelu=True).float()
+    ref = torch.nn.functional.gelu(base)
+    assert (out - ref).abs().max().item() <= 2e-2
+    # bias + fp32 residual -> fp32
+    out = _gemm(lib, A, W, bias=bias, res=res32, out_fp32=True)
+    assert (out - (base + res32)).abs().max().item() <= 2e-3 * base.abs().max().item()
+    # bf16 residual -> bf16
+    out = _gemm(lib, A, W, bias=bias, res=res16).float()
+    assert (out - (base + res16.float())).abs().max().item() <= 5e-2
+
+
+@pytest.mark.parametrize("stride,B,T,C,N", [(1, 2, 3000, 128, 384), (2, 2, 3000, 384, 384), (1, 1, 200, 64, 128), (2, 3, 256, 128, 256)])
+def test_conv1d(lib, cuda_device, stride, B, T, C, N):
+    g = torch.Generator(device="cpu").manual_seed(11 + stride)
+    x = (torch.randn(B, T, C, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    w = (torch.randn(N, C, 3, generator=g) * 0.05).to(torch.bfloat16).to(cuda_device)  # torch layout
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    T_out = T // stride
+    addend = torch.randn(T_out, N, generator=g).to(cuda_device)
+    w_tap = w.permute(0, 2, 1).contiguous().view(N, 3 * C)
+    out = torch.zeros((B, T_out, N), dtype=torch.float32, device=cuda_device)
+    _lib.check(lib.b200w_conv1d_k3(x.data_ptr(), w_tap.data_ptr(), bias.data_ptr(), addend.data_ptr(),
+                                   out.data_ptr(), B, T, C, N, stride, 1,
+                                   torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), bias, stride=stride, padding=1)
+    ref = torch.nn.functional.gelu(ref).transpose(1, 2) + addend
+    err = (out - ref).abs().max().item()
+    assert err <= 5e-3, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 1500, 6), (2, 1500, 2), (1, 128, 1), (2, 333, 4)])
+def test_enc_attention(lib, cuda_device, B, T, H):
+    d = H * 64
+    g = torch.Generator(device="cpu").manual_seed(B * 100 + T)
+    qkv = (torch.randn(B, T, 3 * d, generator=g)).to(torch.bfloat16).to(cuda_device)
+    out = torch.zeros((B, T, d), dtype=torch.bfloat16, device=cuda_device)
+    _lib.check(lib.b200w_enc_attention(qkv.data_ptr(), B, T, d, H, out.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().split(d, dim=-1)
+    q = q.view(B, T, H, 64).transpose(1, 2)
+    k = k.view(B, T, H, 64).transpose(1, 2)
+    v = v.view(B, T, H, 64).transpose(1, 2)
+    ref = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v
+    ref = ref.transpose(1, 2).reshape(B, T, d)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2, f"max abs err {err}"
