@@ -1,17 +1,914 @@
-// placeholder, replaced below
+// Whisper engine: encoder, cross-K/V, autoregressive decode (greedy / beam, Whisper logit rules,
+// token-granular paged KV cache), word-timing pass and language detection, orchestrated in C++
+// over the kernels of this library.  Replaces the CTranslate2 runtime the reference reaches
+// through faster-whisper (/root/reference/asr_components.py:279-288).
+//
+// KV cache layout ("pages" of one token): per decoder layer two pools K,V bf16 [slots][d].  A
+// hypothesis is a row of a page table (int32 [rows][n_text_ctx], position -> slot).  Prompt slots
+// are written once per chunk and shared by every beam; a beam step writes one fresh slot per
+// hypothesis and forks by copying table rows (ints), never K/V bytes.
 #include "../../include/b200w.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "attention.h"
 #include "common.h"
+#include "gemm.h"
+#include "kernels.h"
+
 using namespace b200w;
-#define NI(name) { set_last_error(name " not implemented yet"); return -1; }
-extern "C" {
-int b200w_engine_create(const b200w_model_config*, b200w_engine**) NI("engine_create")
-int b200w_engine_destroy(b200w_engine*) NI("engine_destroy")
-int b200w_engine_set_weight(b200w_engine*, const char*, const void*, int64_t, int) NI("set_weight")
-int b200w_engine_finalize(b200w_engine*) NI("finalize")
-int b200w_encode(b200w_engine*, const void*, int, void*, void*) NI("encode")
-int b200w_cross_kv(b200w_engine*, const void*, int, void*, void*) NI("cross_kv")
-int b200w_decode(b200w_engine*, const void*, int, const int32_t*, const int32_t*, const b200w_decode_opts*, int32_t*, int32_t, int32_t*, float*, float*, void*) NI("decode")
-int b200w_align(b200w_engine*, const void*, int, const int32_t*, const int32_t*, const int32_t*, int32_t, const int32_t*, int32_t, int32_t, int32_t*, int32_t, int32_t*, float*, int32_t, void*) NI("align")
-int b200w_detect_language(b200w_engine*, const void*, int, int32_t, const int32_t*, int32_t, float*, void*) NI("detect_language")
-int b200w_decoder_logits(b200w_engine*, const void*, int, const int32_t*, const int32_t*, float*, void*) NI("decoder_logits")
+
+namespace {
+
+struct Weight {
+  const void* ptr;
+  int64_t numel;
+  int dtype;  // 0 fp32, 1 bf16
+};
+
+struct Lin {
+  const bf16* w = nullptr;
+  const float* b = nullptr;
+};
+struct Norm {
+  const float* g = nullptr;
+  const float* b = nullptr;
+};
+struct EncLayer {
+  Norm ln1, ln2;
+  Lin qkv, out, fc1, fc2;
+};
+struct DecLayer {
+  Norm ln1, ln2, ln3;
+  Lin qkv, out, cq, cout, fc1, fc2;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void alloc(size_t n) {
+    if (n > bytes) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      B200W_CHECK_CUDA(cudaMalloc(&p, n));
+      bytes = n;
+    }
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void alloc(size_t n) {
+    if (n > bytes) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      B200W_CHECK_CUDA(cudaMallocHost(&p, n));
+      bytes = n;
+    }
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct b200w_engine {
+  b200w_model_config cfg{};
+  std::unordered_map<std::string, Weight> weights;
+  bool finalized = false;
+
+  // resolved weights
+  Lin conv1, conv2;
+  const float* enc_pos = nullptr;
+  std::vector<EncLayer> enc;
+  Norm enc_ln_post;
+  const bf16* tok_emb = nullptr;
+  const float* dec_pos = nullptr;
+  std::vector<DecLayer> dec;
+  Lin cross_kv;
+  Norm dec_ln;
+
+  int d = 0, H = 0, Le = 0, Ld = 0, V = 0, ldv = 0, Tctx = 0, Tenc = 0;
+  int n_max = 0;       // max decoder tokens per forward pass
+  int slots_per_stream = 0;
+  int logit_rows = 0;  // capacity of the logits buffer (rows)
+
+  // workspaces
+  DevBuf e_x, e_h, e_qkv, e_attn, e_mlp;              // encoder
+  DevBuf d_x, d_h, d_qkv, d_attn, d_cq, d_mlp, d_hsel;  // decoder
+  DevBuf kpool, vpool;                                // [Ld][slots][d] bf16 each
+  DevBuf tables[2];                                   // int32 [rows][Tctx]
+  DevBuf logits;                                      // fp32 [logit_rows][ldv]
+  DevBuf meta;                                        // per-pass int metadata
+  DevBuf cross_off, const_len, mask, topk_ids, topk_lp, probs, head_export;
+  DevBuf al_w, al_mat, al_trace, al_path, al_plen, scratch_i;
+  PinnedBuf h_meta, h_out;
+  long long total_slots = 0;
+};
+
+namespace {
+
+const void* need(b200w_engine* e, const std::string& name, int64_t numel, int dtype) {
+  auto it = e->weights.find(name);
+  if (it == e->weights.end()) throw Error("missing weight: " + name);
+  if (it->second.numel != numel || it->second.dtype != dtype) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "weight %s: expected numel %lld dtype %d, got %lld dtype %d", name.c_str(),
+             (long long)numel, dtype, (long long)it->second.numel, it->second.dtype);
+    throw Error(buf);
+  }
+  if (reinterpret_cast<uintptr_t>(it->second.ptr) & 15) throw Error("weight " + name + " is not 16-byte aligned");
+  return it->second.ptr;
 }
+Lin need_lin(b200w_engine* e, const std::string& p, int64_t n, int64_t k) {
+  Lin l;
+  l.w = static_cast<const bf16*>(need(e, p + ".w", n * k, 1));
+  l.b = static_cast<const float*>(need(e, p + ".b", n, 0));
+  return l;
+}
+Norm need_norm(b200w_engine* e, const std::string& p, int64_t d) {
+  Norm n;
+  n.g = static_cast<const float*>(need(e, p + ".g", d, 0));
+  n.b = static_cast<const float*>(need(e, p + ".b", d, 0));
+  return n;
+}
+
+void linear(const bf16* A, int M, int K, const Lin& l, int N, void* out, int64_t ldo, int out_fp32, int act,
+            const void* residual, int res_fp32, int64_t ldr, cudaStream_t s) {
+  GemmDesc g;
+  g.A = A;
+  g.a_rows = M;
+  g.a_cols = K;
+  g.a_row_stride = K;
+  g.W = l.w;
+  g.N = N;
+  g.K = K;
+  g.w_row_stride = K;
+  g.out_rows = M;
+  g.bias = l.b;
+  g.act = act;
+  g.residual = residual;
+  g.res_fp32 = res_fp32;
+  g.res_row_stride = ldr;
+  g.out = out;
+  g.out_fp32 = out_fp32;
+  g.out_row_stride = ldo;
+  gemm_bf16(g, s);
+}
+
+// ----------------------------------------------------------------------------------- decoder pass
+struct PassMeta {  // device pointers into e->meta for one forward pass of n tokens
+  int n = 0;
+  int *tok, *pos, *slot, *trow, *kvlen, *stream, *parent;
+  int4* state;
+};
+
+// host-side staging of the metadata: [tok|pos|slot|trow|kvlen|stream] x n ints, then state int4 x n
+struct HostMeta {
+  std::vector<int> tok, pos, slot, trow, kvlen, stream, parent;
+  std::vector<int4> state;
+  void clear() {
+    tok.clear(); pos.clear(); slot.clear(); trow.clear(); kvlen.clear(); stream.clear(); parent.clear();
+    state.clear();
+  }
+  int n() const { return (int)tok.size(); }
+  void push(int t, int p, int s, int tr, int kl, int st, int4 sstate = make_int4(0, 0, 0, 0), int par = 0) {
+    tok.push_back(t); pos.push_back(p); slot.push_back(s); trow.push_back(tr); kvlen.push_back(kl);
+    stream.push_back(st); parent.push_back(par); state.push_back(sstate);
+  }
+};
+
+PassMeta upload_meta(b200w_engine* e, const HostMeta& h, cudaStream_t s) {
+  const int n = h.n();
+  B200W_REQUIRE(n <= e->n_max, "too many decoder tokens in one pass");
+  const size_t ints = (size_t)n * 7, bytes = ints * 4 + (size_t)n * 16 + 16;
+  e->h_meta.alloc(bytes);
+  int* hp = e->h_meta.as<int>();
+  memcpy(hp, h.tok.data(), n * 4);
+  memcpy(hp + n, h.pos.data(), n * 4);
+  memcpy(hp + 2 * n, h.slot.data(), n * 4);
+  memcpy(hp + 3 * n, h.trow.data(), n * 4);
+  memcpy(hp + 4 * n, h.kvlen.data(), n * 4);
+  memcpy(hp + 5 * n, h.stream.data(), n * 4);
+  memcpy(hp + 6 * n, h.parent.data(), n * 4);
+  const size_t st_off = (ints * 4 + 15) / 16 * 16;
+  memcpy(reinterpret_cast<char*>(hp) + st_off, h.state.data(), (size_t)n * 16);
+  B200W_CHECK_CUDA(cudaMemcpyAsync(e->meta.p, hp, st_off + (size_t)n * 16, cudaMemcpyHostToDevice, s));
+  PassMeta m;
+  m.n = n;
+  int* dp = e->meta.as<int>();
+  m.tok = dp; m.pos = dp + n; m.slot = dp + 2 * n; m.trow = dp + 3 * n; m.kvlen = dp + 4 * n;
+  m.stream = dp + 5 * n;
+  m.parent = dp + 6 * n;
+  m.state = reinterpret_cast<int4*>(reinterpret_cast<char*>(dp) + st_off);
+  return m;
+}
+
+struct AlignExport {
+  float* probs = nullptr;           // [n_align][n][Tenc]
+  const int* head_table = nullptr;  // device [Ld][H] -> export index or -1
+  std::vector<char> layer_has;      // host: any exported head in layer l
+};
+
+// Run every decoder layer over n tokens; hidden state (pre final-LN) ends up in e->d_x (fp32).
+void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, const int* table,
+                     int max_kvlen, const AlignExport* ax, cudaStream_t s) {
+  const int n = m.n, d = e->d;
+  float* x = e->d_x.as<float>();
+  bf16* h = e->d_h.as<bf16>();
+  bf16* qkv = e->d_qkv.as<bf16>();
+  bf16* attn = e->d_attn.as<bf16>();
+  bf16* cq = e->d_cq.as<bf16>();
+  bf16* mlp = e->d_mlp.as<bf16>();
+  embed_tokens(m.tok, m.pos, e->tok_emb, e->dec_pos, x, n, d, s);
+  for (int l = 0; l < e->Ld; ++l) {
+    const DecLayer& L = e->dec[l];
+    bf16* kp = e->kpool.as<bf16>() + (long long)l * e->total_slots * d;
+    bf16* vp = e->vpool.as<bf16>() + (long long)l * e->total_slots * d;
+    // self attention
+    layernorm(x, nullptr, L.ln1.g, L.ln1.b, h, n, d, s);
+    linear(h, n, d, L.qkv, 3 * d, qkv, 3 * d, 0, 0, nullptr, 0, 0, s);
+    kv_scatter(qkv, m.slot, kp, vp, n, d, s);
+    DecAttnParams a;
+    a.q = qkv; a.q_stride = 3 * d;
+    a.kbase = kp; a.vbase = vp; a.kv_row_stride = d;
+    a.table = table; a.table_stride = e->Tctx; a.trow = m.trow; a.kvlen = m.kvlen;
+    a.out = attn; a.out_stride = d; a.scale = 0.125f; a.n_queries = n; a.max_len = max_kvlen;
+    dec_attention(a, e->H, s);
+    linear(attn, n, d, L.out, d, x, d, 1, 0, x, 1, d, s);
+    // cross attention
+    layernorm(x, nullptr, L.ln2.g, L.ln2.b, h, n, d, s);
+    linear(h, n, d, L.cq, d, cq, d, 0, 0, nullptr, 0, 0, s);
+    DecAttnParams c;
+    c.q = cq; c.q_stride = d;
+    c.kbase = cross_kv + (long long)l * 2 * d;
+    c.vbase = cross_kv + (long long)l * 2 * d + d;
+    c.kv_row_stride = (long long)e->Ld * 2 * d;
+    c.table = nullptr; c.trow = m.stream; c.kv_base_off = e->cross_off.as<long long>();
+    c.kvlen = e->const_len.as<int>();
+    c.out = attn; c.out_stride = d; c.scale = 0.125f; c.n_queries = n; c.max_len = e->Tenc;
+    if (ax && ax->layer_has[l]) {
+      c.head_export = ax->head_table + (long long)l * e->H;
+      c.probs_out = ax->probs;
+      c.probs_stride = e->Tenc;
+    }
+    dec_attention(c, e->H, s);
+    linear(attn, n, d, L.cout, d, x, d, 1, 0, x, 1, d, s);
+    // MLP
+    layernorm(x, nullptr, L.ln3.g, L.ln3.b, h, n, d, s);
+    linear(h, n, d, L.fc1, 4 * d, mlp, 4 * d, 0, 1, nullptr, 0, 0, s);
+    linear(mlp, n, 4 * d, L.fc2, d, x, d, 1, 0, x, 1, d, s);
+  }
+}
+
+// final LayerNorm on selected rows + tied-embedding logits -> e->logits[0 .. n_sel)
+void logits_for_rows(b200w_engine* e, const int* sel_rows_dev, int n_sel, cudaStream_t s) {
+  B200W_REQUIRE(n_sel <= e->logit_rows, "logits buffer too small");
+  bf16* hsel = e->d_hsel.as<bf16>();
+  layernorm(e->d_x.as<float>(), sel_rows_dev, e->dec_ln.g, e->dec_ln.b, hsel, n_sel, e->d, s);
+  Lin emb;
+  emb.w = e->tok_emb;
+  emb.b = nullptr;
+  linear(hsel, n_sel, e->d, emb, e->V, e->logits.p, e->ldv, 1, 0, nullptr, 0, 0, s);
+}
+
+void upload_ints(int* dst, const std::vector<int>& v, cudaStream_t s) {
+  if (v.empty()) return;
+  B200W_CHECK_CUDA(cudaMemcpyAsync(dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice, s));
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200w_engine_create(const b200w_model_config* cfg, b200w_engine** out) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(cfg && out, "null argument");
+  B200W_REQUIRE(cfg->d_model % 128 == 0 && cfg->d_model <= 1280 && cfg->n_heads * 64 == cfg->d_model,
+                "d_model must be a multiple of 128 (<= 1280) with 64-wide heads");
+  B200W_REQUIRE(cfg->n_mels == 80 || cfg->n_mels == 128, "n_mels must be 80 or 128");
+  B200W_REQUIRE(cfg->n_audio_ctx == 1500 && cfg->n_text_ctx >= 8 && cfg->n_text_ctx <= 448, "context sizes");
+  B200W_REQUIRE(cfg->max_batch >= 1 && cfg->max_beam >= 1 && 2 * cfg->max_beam <= MAX_TOPK, "batch / beam limits");
+  int ndev = 0;
+  B200W_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+  B200W_REQUIRE(ndev > 0, "no CUDA device (there is no CPU fallback)");
+  b200w_engine* e = new b200w_engine();
+  e->cfg = *cfg;
+  e->d = cfg->d_model; e->H = cfg->n_heads; e->Le = cfg->n_enc_layers; e->Ld = cfg->n_dec_layers;
+  e->V = cfg->n_vocab; e->ldv = (cfg->n_vocab + 7) / 8 * 8; e->Tctx = cfg->n_text_ctx; e->Tenc = cfg->n_audio_ctx;
+  *out = e;
+  B200W_API_END
+}
+
+int b200w_engine_destroy(b200w_engine* e) {
+  B200W_API_BEGIN
+  if (e) {
+    DevBuf* bufs[] = {&e->e_x, &e->e_h, &e->e_qkv, &e->e_attn, &e->e_mlp, &e->d_x, &e->d_h, &e->d_qkv,
+                      &e->d_attn, &e->d_cq, &e->d_mlp, &e->d_hsel, &e->kpool, &e->vpool, &e->tables[0],
+                      &e->tables[1], &e->logits, &e->meta, &e->cross_off, &e->const_len, &e->mask,
+                      &e->topk_ids, &e->topk_lp, &e->probs, &e->head_export, &e->al_w, &e->al_mat,
+                      &e->al_trace, &e->al_path, &e->al_plen, &e->scratch_i};
+    for (DevBuf* b : bufs) b->release();
+    e->h_meta.release();
+    e->h_out.release();
+    delete e;
+  }
+  B200W_API_END
+}
+
+int b200w_engine_set_weight(b200w_engine* e, const char* name, const void* dev_ptr, int64_t numel, int dtype) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(e && name && dev_ptr, "null argument");
+  B200W_REQUIRE(!e->finalized, "engine already finalized");
+  e->weights[name] = Weight{dev_ptr, numel, dtype};
+  B200W_API_END
+}
+
+int b200w_engine_finalize(b200w_engine* e) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(e, "null engine");
+  const int64_t d = e->d;
+  e->conv1 = need_lin(e, "enc.conv1", d, 3 * 128);
+  e->conv2 = need_lin(e, "enc.conv2", d, 3 * d);
+  e->enc_pos = static_cast<const float*>(need(e, "enc.pos", (int64_t)e->Tenc * d, 0));
+  e->enc.resize(e->Le);
+  for (int l = 0; l < e->Le; ++l) {
+    const std::string p = "enc.L" + std::to_string(l);
+    EncLayer& L = e->enc[l];
+    L.ln1 = need_norm(e, p + ".ln1", d);
+    L.qkv = need_lin(e, p + ".qkv", 3 * d, d);
+    L.out = need_lin(e, p + ".out", d, d);
+    L.ln2 = need_norm(e, p + ".ln2", d);
+    L.fc1 = need_lin(e, p + ".fc1", 4 * d, d);
+    L.fc2 = need_lin(e, p + ".fc2", d, 4 * d);
+  }
+  e->enc_ln_post = need_norm(e, "enc.ln_post", d);
+  e->tok_emb = static_cast<const bf16*>(need(e, "dec.tok_emb", (int64_t)e->V * d, 1));
+  e->dec_pos = static_cast<const float*>(need(e, "dec.pos", (int64_t)e->Tctx * d, 0));
+  e->dec.resize(e->Ld);
+  for (int l = 0; l < e->Ld; ++l) {
+    const std::string p = "dec.L" + std::to_string(l);
+    DecLayer& L = e->dec[l];
+    L.ln1 = need_norm(e, p + ".ln1", d);
+    L.qkv = need_lin(e, p + ".qkv", 3 * d, d);
+    L.out = need_lin(e, p + ".out", d, d);
+    L.ln2 = need_norm(e, p + ".ln2", d);
+    L.cq = need_lin(e, p + ".cq", d, d);
+    L.cout = need_lin(e, p + ".cout", d, d);
+    L.ln3 = need_norm(e, p + ".ln3", d);
+    L.fc1 = need_lin(e, p + ".fc1", 4 * d, d);
+    L.fc2 = need_lin(e, p + ".fc2", d, 4 * d);
+  }
+  e->cross_kv = need_lin(e, "dec.cross_kv", (int64_t)e->Ld * 2 * d, d);
+  e->dec_ln = need_norm(e, "dec.ln", d);
+
+  const int64_t Bm = e->cfg.max_batch, T = e->Tenc;
+  e->e_x.alloc(Bm * T * d * 4);
+  e->e_h.alloc(Bm * T * d * 2);
+  e->e_qkv.alloc(Bm * T * 3 * d * 2);
+  e->e_attn.alloc(Bm * T * d * 2);
+  e->e_mlp.alloc(Bm * T * 4 * d * 2);  // also holds conv1's output [3000][d]
+  e->n_max = (int)(Bm * e->Tctx);
+  const int64_t n = e->n_max;
+  e->d_x.alloc(n * d * 4);
+  e->d_h.alloc(n * d * 2);
+  e->d_qkv.alloc(n * 3 * d * 2);
+  e->d_attn.alloc(n * d * 2);
+  e->d_cq.alloc(n * d * 2);
+  e->d_mlp.alloc(n * 4 * d * 2);
+  e->slots_per_stream = e->Tctx * e->cfg.max_beam;
+  e->total_slots = (long long)e->slots_per_stream * Bm;
+  e->kpool.alloc((size_t)e->Ld * e->total_slots * d * 2);
+  e->vpool.alloc((size_t)e->Ld * e->total_slots * d * 2);
+  const int64_t rows = Bm * e->cfg.max_beam;
+  e->tables[0].alloc(rows * e->Tctx * 4);
+  e->tables[1].alloc(rows * e->Tctx * 4);
+  e->logit_rows = (int)std::max<int64_t>(2 * rows, 1024);
+  e->logits.alloc((size_t)e->logit_rows * e->ldv * 4);
+  e->d_hsel.alloc((size_t)e->logit_rows * d * 2);
+  e->meta.alloc((size_t)n * 7 * 4 + (size_t)n * 16 + 64);
+  e->scratch_i.alloc(((size_t)e->logit_rows + 4 * Bm + n) * 4);
+  e->cross_off.alloc(Bm * 8);
+  e->const_len.alloc(n * 4);
+  e->mask.alloc(e->V);
+  e->topk_ids.alloc(rows * MAX_TOPK * 4);
+  e->topk_lp.alloc(rows * MAX_TOPK * 4);
+  e->probs.alloc(std::max<int64_t>(n, Bm * 128) * 4);
+  e->head_export.alloc((size_t)e->Ld * e->H * 4);
+  {
+    std::vector<long long> off(Bm);
+    for (int64_t b = 0; b < Bm; ++b) off[b] = b * T * e->Ld * 2 * d;
+    B200W_CHECK_CUDA(cudaMemcpy(e->cross_off.p, off.data(), Bm * 8, cudaMemcpyHostToDevice));
+    std::vector<int> cl(n, (int)T);
+    B200W_CHECK_CUDA(cudaMemcpy(e->const_len.p, cl.data(), n * 4, cudaMemcpyHostToDevice));
+  }
+  e->finalized = true;
+  B200W_API_END
+}
+
+int b200w_encode(b200w_engine* e, const void* windows_dev, int B, void* enc_out_dev, void* stream) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int d = e->d, T = e->Tenc, M = B * T;
+  float* x = e->e_x.as<float>();
+  bf16* h = e->e_h.as<bf16>();
+  bf16* qkv = e->e_qkv.as<bf16>();
+  bf16* attn = e->e_attn.as<bf16>();
+  bf16* mlp = e->e_mlp.as<bf16>();
+  bf16* x1 = mlp;  // conv1 output [B][3000][d], dead before the first MLP
+  conv1d_k3(static_cast<const bf16*>(windows_dev), e->conv1.w, e->conv1.b, nullptr, x1, B, 2 * T, 128, d, 1, 0, s);
+  conv1d_k3(x1, e->conv2.w, e->conv2.b, e->enc_pos, x, B, 2 * T, d, d, 2, 1, s);
+  for (int l = 0; l < e->Le; ++l) {
+    const EncLayer& L = e->enc[l];
+    layernorm(x, nullptr, L.ln1.g, L.ln1.b, h, M, d, s);
+    linear(h, M, d, L.qkv, 3 * d, qkv, 3 * d, 0, 0, nullptr, 0, 0, s);
+    enc_attention(qkv, B, T, d, e->H, attn, s);
+    linear(attn, M, d, L.out, d, x, d, 1, 0, x, 1, d, s);
+    layernorm(x, nullptr, L.ln2.g, L.ln2.b, h, M, d, s);
+    linear(h, M, d, L.fc1, 4 * d, mlp, 4 * d, 0, 1, nullptr, 0, 0, s);
+    linear(mlp, M, 4 * d, L.fc2, d, x, d, 1, 0, x, 1, d, s);
+  }
+  layernorm(x, nullptr, e->enc_ln_post.g, e->enc_ln_post.b, static_cast<bf16*>(enc_out_dev), M, d, s);
+  B200W_API_END
+}
+
+int b200w_cross_kv(b200w_engine* e, const void* enc_out_dev, int B, void* cross_kv_dev, void* stream) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
+  const int N = e->Ld * 2 * e->d;
+  linear(static_cast<const bf16*>(enc_out_dev), B * e->Tenc, e->d, e->cross_kv, N, cross_kv_dev, N, 0, 0,
+         nullptr, 0, 0, static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
+// -------------------------------------------------------------------------------------- decode
+namespace {
+
+struct Hyp {
+  std::vector<int> tokens;  // sampled tokens (no prompt)
+  double cum = 0.0;
+  int table_row = 0;
+};
+struct Finished {
+  std::vector<int> tokens;  // without EOT
+  double cum = 0.0;
+  double score = 0.0;
+};
+struct StreamState {
+  int P = 0;            // prompt length
+  int max_new = 0;
+  bool done = false;
+  std::vector<Hyp> alive;
+  std::vector<Finished> finished;
+};
+
+int4 sampling_state(const std::vector<int>& toks, const b200w_decode_opts& o) {
+  int flags = 0, ts_lo = 0;
+  if (!o.without_timestamps) flags |= SF_RULES;
+  const int n = (int)toks.size();
+  if (n == 0) flags |= SF_FIRST;
+  if (!o.without_timestamps && n > 0) {
+    const bool last_ts = toks[n - 1] >= o.timestamp_begin;
+    const bool pen_ts = n < 2 || toks[n - 2] >= o.timestamp_begin;
+    if (last_ts) flags |= pen_ts ? SF_SUP_ALL_TS : SF_SUP_TEXT;
+    int last_stamp = -1;
+    for (int i = n - 1; i >= 0; --i)
+      if (toks[i] >= o.timestamp_begin) { last_stamp = toks[i]; break; }
+    if (last_stamp >= 0) ts_lo = (last_ts && !pen_ts) ? last_stamp : last_stamp + 1;
+  }
+  return make_int4(flags, ts_lo, 0, 0);
+}
+
+double norm_score(double cum, int len, float lp) {
+  return cum / pow((double)std::max(len, 1), (double)lp);
+}
+
+}  // namespace
+
+int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t* prompts_host,
+                 const int32_t* prompt_lens_host, const b200w_decode_opts* opts, int32_t* tokens_out_host,
+                 int32_t max_out, int32_t* n_tokens_out_host, float* sum_logprob_out_host,
+                 float* no_speech_out_host, void* stream) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
+  B200W_REQUIRE(opts && opts->beam_size >= 1 && opts->beam_size <= e->cfg.max_beam, "beam size out of range");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const b200w_decode_opts& o = *opts;
+  const int K = o.beam_size, k_top = K == 1 ? 1 : 2 * K;
+  const bf16* ckv = static_cast<const bf16*>(cross_kv_dev);
+  const int Tctx = e->Tctx;
+  const int max_cand = std::max(1, (int)lround(K * (double)o.patience));
+
+  // static masks: bit0 suppress list, bit1 first-position blanks
+  {
+    std::vector<unsigned char> mk(e->V, 0);
+    for (int i = 0; i < o.n_suppress; ++i)
+      if (o.suppress_ids[i] >= 0 && o.suppress_ids[i] < e->V) mk[o.suppress_ids[i]] |= 1;
+    if (o.suppress_blank)
+      for (int i = 0; i < o.n_blank; ++i)
+        if (o.blank_ids[i] >= 0 && o.blank_ids[i] < e->V) mk[o.blank_ids[i]] |= 2;
+    B200W_CHECK_CUDA(cudaMemcpyAsync(e->mask.p, mk.data(), e->V, cudaMemcpyHostToDevice, s));
+    B200W_CHECK_CUDA(cudaStreamSynchronize(s));  // mk goes out of scope
+  }
+
+  // ---- prefill: every prompt token of every stream in one pass
+  std::vector<StreamState> st(B);
+  HostMeta hm;
+  std::vector<int> sel_rows, sot_rows(B, -1);
+  std::vector<int> table0((size_t)B * K * Tctx, 0);
+  int off = 0, max_P = 0;
+  for (int b = 0; b < B; ++b) {
+    const int P = prompt_lens_host[b];
+    B200W_REQUIRE(P >= 1 && P < Tctx, "prompt length out of range");
+    st[b].P = P;
+    st[b].max_new = Tctx - P;
+    if (o.max_new_tokens > 0) st[b].max_new = std::min(st[b].max_new, (int)o.max_new_tokens);
+    max_P = std::max(max_P, P);
+    const int slot0 = b * e->slots_per_stream;
+    for (int i = 0; i < P; ++i) {
+      const int t = prompts_host[off + i];
+      B200W_REQUIRE(t >= 0 && t < e->V, "prompt token out of range");
+      if (t == o.sot) sot_rows[b] = hm.n();
+      hm.push(t, i, slot0 + i, b * K, i + 1, b);
+      for (int k = 0; k < K; ++k) table0[((size_t)b * K + k) * Tctx + i] = slot0 + i;
+    }
+    sel_rows.push_back(hm.n() - 1);  // logits at the last prompt position
+    off += P;
+  }
+  for (int b = 0; b < B; ++b) sel_rows.push_back(sot_rows[b] >= 0 ? sot_rows[b] : sel_rows[b]);
+  int cur = 0;
+  B200W_CHECK_CUDA(cudaMemcpyAsync(e->tables[cur].p, table0.data(), table0.size() * 4, cudaMemcpyHostToDevice, s));
+  PassMeta pm = upload_meta(e, hm, s);
+  decoder_forward(e, ckv, pm, e->tables[cur].as<int>(), max_P, nullptr, s);
+  // selected rows: [last position x B | sot position x B]
+  int* sel_dev = e->scratch_i.as<int>();
+  upload_ints(sel_dev, sel_rows, s);
+  logits_for_rows(e, sel_dev, 2 * B, s);
+  // no-speech probability from the raw logits at <|startoftranscript|>
+  std::vector<int> ns_tok(B, o.no_speech), ns_rows(B);
+  for (int b = 0; b < B; ++b) ns_rows[b] = B + b;
+  int* ns_dev = e->scratch_i.as<int>() + 2 * B;
+  upload_ints(ns_dev, ns_rows, s);
+  upload_ints(ns_dev + B, ns_tok, s);
+  token_probs(e->logits.as<float>(), e->ldv, e->V, ns_dev, ns_dev + B, nullptr, 0, e->probs.as<float>(), B, s);
+  e->h_out.alloc(std::max<size_t>((size_t)B * K * MAX_TOPK * 8, (size_t)B * 4) + 64);
+  B200W_CHECK_CUDA(cudaMemcpyAsync(e->h_out.p, e->probs.p, B * 4, cudaMemcpyDeviceToHost, s));
+  B200W_CHECK_CUDA(cudaStreamSynchronize(s));
+  for (int b = 0; b < B; ++b) no_speech_out_host[b] = e->h_out.as<float>()[b];
+
+  // ---- first sampled position: one logits row per stream (rows 0..B of e->logits)
+  std::vector<int4> sstate(B);
+  for (int b = 0; b < B; ++b) sstate[b] = sampling_state({}, o);
+  int4* state_dev = reinterpret_cast<int4*>(e->meta.p);  // reuse: the pass metadata is consumed
+  B200W_CHECK_CUDA(cudaMemcpyAsync(state_dev, sstate.data(), B * 16, cudaMemcpyHostToDevice, s));
+  SampleParams sp;
+  sp.logits = e->logits.as<float>(); sp.ld = e->ldv; sp.n_vocab = e->V;
+  sp.mask = e->mask.as<unsigned char>(); sp.state = state_dev;
+  sp.eot = o.eot; sp.no_timestamps = o.no_timestamps; sp.timestamp_begin = o.timestamp_begin;
+  sp.max_initial_ts = o.max_initial_timestamp_index; sp.k = k_top;
+  sp.out_ids = e->topk_ids.as<int>(); sp.out_logprobs = e->topk_lp.as<float>();
+  sample_topk(sp, B, s);
+  int* h_ids = e->h_out.as<int>();
+  float* h_lp = reinterpret_cast<float*>(h_ids + (size_t)B * K * MAX_TOPK);
+  B200W_CHECK_CUDA(cudaMemcpyAsync(h_ids, sp.out_ids, (size_t)B * k_top * 4, cudaMemcpyDeviceToHost, s));
+  B200W_CHECK_CUDA(cudaMemcpyAsync(h_lp, sp.out_logprobs, (size_t)B * k_top * 4, cudaMemcpyDeviceToHost, s));
+  B200W_CHECK_CUDA(cudaStreamSynchronize(s));
+
+  auto finish_stream = [&](StreamState& S) {
+    // out of budget: every live hypothesis ends here (no EOT was produced)
+    for (Hyp& h : S.alive) {
+      Finished f;
+      f.tokens = h.tokens;
+      f.cum = h.cum;
+      f.score = norm_score(h.cum, (int)h.tokens.size(), o.length_penalty);
+      S.finished.push_back(std::move(f));
+    }
+    S.alive.clear();
+    S.done = true;
+  };
+
+  for (int b = 0; b < B; ++b) {
+    StreamState& S = st[b];
+    for (int c = 0; c < k_top && (int)S.alive.size() < K; ++c) {
+      const int tok = h_ids[b * k_top + c];
+      const float lp = h_lp[b * k_top + c];
+      if (tok == 0x7fffffff || !(lp > -INFINITY)) continue;
+      if (tok == o.eot) {
+        if ((int)S.finished.size() < max_cand) {
+          Finished f;
+          f.cum = lp;
+          f.score = norm_score(lp, 0, o.length_penalty);
+          S.finished.push_back(f);
+        }
+        continue;
+      }
+      Hyp h;
+      h.tokens.push_back(tok);
+      h.cum = lp;
+      h.table_row = b * K + (int)S.alive.size();
+      S.alive.push_back(std::move(h));
+    }
+    if (S.alive.empty() || (int)S.finished.size() >= max_cand) S.done = true;
+    if (!S.done && S.max_new <= 1) finish_stream(S);
+  }
+
+  // ---- autoregressive steps
+  for (int step = 1;; ++step) {
+    hm.clear();
+    struct RowRef { int b, k; };
+    std::vector<RowRef> rows;
+    int max_kv = 0;
+    for (int b = 0; b < B; ++b) {
+      StreamState& S = st[b];
+      if (S.done) continue;
+      for (int k = 0; k < (int)S.alive.size(); ++k) {
+        Hyp& h = S.alive[k];
+        const int pos = S.P + step - 1;
+        const int slot = b * e->slots_per_stream + S.P + (step - 1) * K + k;
+        const int new_row = b * K + k;
+        hm.push(h.tokens.back(), pos, slot, new_row, pos + 1, b, sampling_state(h.tokens, o), h.table_row);
+        h.table_row = new_row;
+        rows.push_back({b, k});
+        max_kv = std::max(max_kv, pos + 1);
+      }
+    }
+    const int n = hm.n();
+    if (n == 0) break;
+    pm = upload_meta(e, hm, s);
+    // fork the page tables: new[row] = old[parent][0:pos] + [slot]
+    {
+      const int nxt = cur ^ 1;
+      gather_fork_tables(e->tables[cur].as<int>(), pm.parent, pm.trow, pm.pos, pm.slot,
+                         e->tables[nxt].as<int>(), n, Tctx, s);
+      cur = nxt;
+    }
+    decoder_forward(e, ckv, pm, e->tables[cur].as<int>(), max_kv, nullptr, s);
+    logits_for_rows(e, nullptr, n, s);
+    sp.state = pm.state;
+    sample_topk(sp, n, s);
+    B200W_CHECK_CUDA(cudaMemcpyAsync(h_ids, sp.out_ids, (size_t)n * k_top * 4, cudaMemcpyDeviceToHost, s));
+    B200W_CHECK_CUDA(cudaMemcpyAsync(h_lp, sp.out_logprobs, (size_t)n * k_top * 4, cudaMemcpyDeviceToHost, s));
+    B200W_CHECK_CUDA(cudaStreamSynchronize(s));
+
+    // host-side beam bookkeeping
+    int r0 = 0;
+    for (int b = 0; b < B; ++b) {
+      StreamState& S = st[b];
+      if (S.done) continue;
+      const int na = (int)S.alive.size();
+      struct Cand { double score; int k, tok; float lp; };
+      std::vector<Cand> cands;
+      cands.reserve((size_t)na * k_top);
+      for (int k = 0; k < na; ++k)
+        for (int c = 0; c < k_top; ++c) {
+          const int tok = h_ids[(r0 + k) * k_top + c];
+          const float lp = h_lp[(r0 + k) * k_top + c];
+          if (tok == 0x7fffffff || !(lp > -INFINITY)) continue;
+          cands.push_back({S.alive[k].cum + (double)lp, k, tok, lp});
+        }
+      r0 += na;
+      std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& c) {
+        if (a.score != c.score) return a.score > c.score;
+        if (a.k != c.k) return a.k < c.k;
+        return a.tok < c.tok;
+      });
+      std::vector<Hyp> next;
+      const int limit = std::min((int)cands.size(), k_top);
+      for (int c = 0; c < limit && (int)next.size() < K; ++c) {
+        const Cand& cd = cands[c];
+        const Hyp& par = S.alive[cd.k];
+        if (cd.tok == o.eot) {
+          if ((int)S.finished.size() < max_cand) {
+            Finished f;
+            f.tokens = par.tokens;
+            f.cum = cd.score;
+            f.score = norm_score(cd.score, (int)par.tokens.size(), o.length_penalty);
+            S.finished.push_back(std::move(f));
+          }
+          continue;
+        }
+        Hyp h;
+        h.tokens = par.tokens;
+        h.tokens.push_back(cd.tok);
+        h.cum = cd.score;
+        h.table_row = par.table_row;
+        next.push_back(std::move(h));
+      }
+      S.alive.swap(next);
+      if (S.alive.empty() || (int)S.finished.size() >= max_cand) { S.done = true; continue; }
+      if (step + 1 >= S.max_new) finish_stream(S);
+    }
+  }
+
+  for (int b = 0; b < B; ++b) {
+    StreamState& S = st[b];
+    const Finished* best = nullptr;
+    for (const Finished& f : S.finished)
+      if (!best || f.score > best->score) best = &f;
+    int n = 0;
+    float cum = 0.f;
+    if (best) {
+      n = std::min((int)best->tokens.size(), (int)max_out);
+      for (int i = 0; i < n; ++i) tokens_out_host[(size_t)b * max_out + i] = best->tokens[i];
+      cum = (float)best->cum;
+    }
+    n_tokens_out_host[b] = n;
+    sum_logprob_out_host[b] = cum;
+  }
+  B200W_API_END
+}
+
+int b200w_decoder_logits(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t* tokens_host,
+                         const int32_t* token_lens_host, float* logits_out_dev, void* stream) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HostMeta hm;
+  std::vector<int> table((size_t)B * e->Tctx, 0);
+  int off = 0, maxlen = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = token_lens_host[b];
+    B200W_REQUIRE(n >= 1 && n <= e->Tctx, "sequence length out of range");
+    maxlen = std::max(maxlen, n);
+    for (int i = 0; i < n; ++i) {
+      const int slot = b * e->slots_per_stream + i;
+      hm.push(tokens_host[off + i], i, slot, b, i + 1, b);
+      table[(size_t)b * e->Tctx + i] = slot;
+    }
+    off += n;
+  }
+  B200W_CHECK_CUDA(cudaMemcpyAsync(e->tables[0].p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, s));
+  PassMeta pm = upload_meta(e, hm, s);
+  decoder_forward(e, static_cast<const bf16*>(cross_kv_dev), pm, e->tables[0].as<int>(), maxlen, nullptr, s);
+  B200W_CHECK_CUDA(cudaStreamSynchronize(s));  // host vectors above
+  const int total = hm.n();
+  for (int r0 = 0; r0 < total; r0 += e->logit_rows) {
+    const int nr = std::min(e->logit_rows, total - r0);
+    std::vector<int> rows(nr);
+    for (int i = 0; i < nr; ++i) rows[i] = r0 + i;
+    upload_ints(e->scratch_i.as<int>(), rows, s);
+    logits_for_rows(e, e->scratch_i.as<int>(), nr, s);
+    B200W_CHECK_CUDA(cudaMemcpyAsync(logits_out_dev + (size_t)r0 * e->ldv, e->logits.p,
+                                     (size_t)nr * e->ldv * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  B200W_CHECK_CUDA(cudaStreamSynchronize(s));
+  B200W_API_END
+}
+
+int b200w_detect_language(b200w_engine* e, const void* cross_kv_dev, int B, int32_t sot,
+                          const int32_t* lang_ids_host, int32_t n_lang, float* probs_out_host, void* stream) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch && n_lang >= 1 && n_lang <= 128, "arguments out of range");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HostMeta hm;
+  std::vector<int> table((size_t)B * e->Tctx, 0);
+  for (int b = 0; b < B; ++b) {
+    const int slot = b * e->slots_per_stream;
+    hm.push(sot, 0, slot, b, 1, b);
+    table[(size_t)b * e->Tctx] = slot;
+  }
+  B200W_CHECK_CUDA(cudaMemcpyAsync(e->tables[0].p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, s));
+  PassMeta pm = upload_meta(e, hm, s);
+  decoder_forward(e, static_cast<const bf16*>(cross_kv_dev), pm, e->tables[0].as<int>(), 1, nullptr, s);
+  logits_for_rows(e, nullptr, B, s);
+  std::vector<int> ids(lang_ids_host, lang_ids_host + n_lang);
+  upload_ints(e->scratch_i.as<int>(), ids, s);
+  token_probs(e->logits.as<float>(), e->ldv, e->V, nullptr, nullptr, e->scratch_i.as<int>(), n_lang,
+              e->probs.as<float>(), B, s);
+  e->h_out.alloc((size_t)B * n_lang * 4);
+  B200W_CHECK_CUDA(cudaMemcpyAsync(e->h_out.p, e->probs.p, (size_t)B * n_lang * 4, cudaMemcpyDeviceToHost, s));
+  B200W_CHECK_CUDA(cudaStreamSynchronize(s));
+  memcpy(probs_out_host, e->h_out.p, (size_t)B * n_lang * 4);
+  B200W_API_END
+}
+
+int b200w_align(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t* tokens_host,
+                const int32_t* token_lens_host, const int32_t* num_frames_host, int32_t sot_len,
+                const int32_t* align_heads_host, int32_t n_align, int32_t median_width,
+                int32_t* path_out_host, int32_t max_path, int32_t* path_len_out_host,
+                float* tok_prob_out_host, int32_t max_tok, void* stream) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch && n_align >= 1, "arguments out of range");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Tenc = e->Tenc;
+  HostMeta hm;
+  std::vector<int> table((size_t)B * e->Tctx, 0);
+  std::vector<int> q0(B), ntok(B), nf(B);
+  int off = 0, maxlen = 0, max_nf = 1;
+  for (int b = 0; b < B; ++b) {
+    const int n = token_lens_host[b];
+    B200W_REQUIRE(n >= sot_len + 2 && n <= e->Tctx, "align sequence length out of range");
+    q0[b] = hm.n();
+    ntok[b] = n;
+    nf[b] = std::max(1, std::min(Tenc, num_frames_host[b] / 2));
+    max_nf = std::max(max_nf, nf[b]);
+    maxlen = std::max(maxlen, n);
+    for (int i = 0; i < n; ++i) {
+      const int slot = b * e->slots_per_stream + i;
+      hm.push(tokens_host[off + i], i, slot, b, i + 1, b);
+      table[(size_t)b * e->Tctx + i] = slot;
+    }
+    off += n;
+  }
+  for (int i = 0; i < n_align; ++i)
+    B200W_REQUIRE(align_heads_host[2 * i] >= 0 && align_heads_host[2 * i] < e->Ld &&
+                      align_heads_host[2 * i + 1] >= 0 && align_heads_host[2 * i + 1] < e->H,
+                  "alignment head out of range");
+  const int total = hm.n();
+  B200W_REQUIRE(max_path >= maxlen + max_nf, "max_path too small");
+  e->al_w.alloc((size_t)n_align * total * Tenc * 4);
+  e->al_mat.alloc((size_t)total * Tenc * 4);
+  const long long trace_stride = (long long)(maxlen + 1) * (max_nf + 1);
+  e->al_trace.alloc((size_t)B * trace_stride);
+  e->al_path.alloc((size_t)B * max_path * 8);
+  e->al_plen.alloc((size_t)B * 4 + 12 * (size_t)B);
+  B200W_CHECK_CUDA(cudaMemcpyAsync(e->tables[0].p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, s));
+  PassMeta pm = upload_meta(e, hm, s);
+  AlignExport ax;
+  ax.probs = e->al_w.as<float>();
+  ax.layer_has.assign(e->Ld, 0);
+  {
+    std::vector<int> ht((size_t)e->Ld * e->H, -1);
+    for (int i = 0; i < n_align; ++i) {
+      ht[(size_t)align_heads_host[2 * i] * e->H + align_heads_host[2 * i + 1]] = i;
+      ax.layer_has[align_heads_host[2 * i]] = 1;
+    }
+    upload_ints(e->head_export.as<int>(), ht, s);
+  }
+  ax.head_table = e->head_export.as<int>();
+  decoder_forward(e, static_cast<const bf16*>(cross_kv_dev), pm, e->tables[0].as<int>(), maxlen, &ax, s);
+
+  // seq metadata after path_len: [q0 | ntok | nf]
+  int* plen = e->al_plen.as<int>();
+  int* seq = plen + B;
+  upload_ints(seq, q0, s);
+  upload_ints(seq + B, ntok, s);
+  upload_ints(seq + 2 * B, nf, s);
+  align_postprocess(e->al_w.as<float>(), n_align, total, Tenc, seq, seq + B, seq + 2 * B, B, maxlen, max_nf,
+                    median_width, e->al_mat.as<float>(), sot_len, 1, e->al_trace.as<signed char>(),
+                    trace_stride, e->al_path.as<int>(), max_path, plen, s);
+
+  // teacher-forced probability of every text token: row (sot_len + i) predicts token sot_len + 1 + i
+  std::vector<int> prow, ptok, pcount(B);
+  for (int b = 0; b < B; ++b) {
+    const int n_text = ntok[b] - sot_len - 2;  // minus no_timestamps and eot
+    pcount[b] = std::max(0, std::min(n_text, (int)max_tok));
+    for (int i = 0; i < pcount[b]; ++i) {
+      prow.push_back(q0[b] + sot_len + i);
+      ptok.push_back(hm.tok[q0[b] + sot_len + 1 + i]);
+    }
+  }
+  std::vector<float> probs_host(prow.size());
+  for (size_t r0 = 0; r0 < prow.size(); r0 += e->logit_rows) {
+    const int nr = (int)std::min<size_t>(e->logit_rows, prow.size() - r0);
+    std::vector<int> rr(prow.begin() + r0, prow.begin() + r0 + nr), tt(ptok.begin() + r0, ptok.begin() + r0 + nr);
+    int* scratch = e->scratch_i.as<int>();
+    upload_ints(scratch, rr, s);
+    logits_for_rows(e, scratch, nr, s);
+    upload_ints(scratch, tt, s);
+    token_probs(e->logits.as<float>(), e->ldv, e->V, nullptr, scratch, nullptr, 0, e->probs.as<float>(), nr, s);
+    B200W_CHECK_CUDA(cudaMemcpyAsync(probs_host.data() + r0, e->probs.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, s));
+    B200W_CHECK_CUDA(cudaStreamSynchronize(s));
+  }
+  e->h_out.alloc((size_t)B * max_path * 8 + (size_t)B * 4);
+  B200W_CHECK_CUDA(cudaMemcpyAsync(e->h_out.p, e->al_path.p, (size_t)B * max_path * 8, cudaMemcpyDeviceToHost, s));
+  B200W_CHECK_CUDA(cudaMemcpyAsync(e->h_out.as<char>() + (size_t)B * max_path * 8, plen, (size_t)B * 4,
+                                   cudaMemcpyDeviceToHost, s));
+  B200W_CHECK_CUDA(cudaStreamSynchronize(s));
+  memcpy(path_out_host, e->h_out.p, (size_t)B * max_path * 8);
+  memcpy(path_len_out_host, e->h_out.as<char>() + (size_t)B * max_path * 8, (size_t)B * 4);
+  size_t k = 0;
+  for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < (int)max_tok; ++i) tok_prob_out_host[(size_t)b * max_tok + i] = 0.f;
+    for (int i = 0; i < pcount[b]; ++i) tok_prob_out_host[(size_t)b * max_tok + i] = probs_host[k++];
+  }
+  B200W_API_END
+}
+
+}  // extern "C"

@@ -410,12 +410,15 @@ __global__ void __launch_bounds__(512) dedup_features_kernel(DedupArgs a, int ma
     s_roll = 0x7fffffff;
   }
   __syncthreads();
-  if (plan.n_stages < 0 || M > max_points) {  // unsupported length: NaN marks it (host raises)
+  const int nbins = N / 2 + 1;
+  const bool direct = plan.n_stages < 0;  // a prime factor > RMAX: exact O(N^2) DFT instead
+  const bool fits = direct ? ((long long)N + nbins) * 4 <= (long long)max_points * 8 : M <= max_points;
+  if (!fits) {  // host sized the launch wrongly: NaN marks it (host raises)
     if (tid < 5) out[tid] = __int_as_float(0x7fc00000);
     return;
   }
 
-  // --- time-domain sums (double) and digit-reversed load
+  // --- time-domain sums (double)
   double sumsq = 0.0;
   long long zc = 0;
   for (int i = tid; i < N; i += nthr) {
@@ -423,66 +426,86 @@ __global__ void __launch_bounds__(512) dedup_features_kernel(DedupArgs a, int ma
     sumsq += (double)v * (double)v;
     if (i + 1 < N) zc += (signbit(v) != signbit(__ldg(x + i + 1))) ? 1 : 0;
   }
-  for (int n = tid; n < M; n += nthr) {
-    // position of input n: mixed-radix digit reversal (first radix = outermost stage)
-    int rem = n, pos = 0, blk = M;
-    for (int st = 0; st < plan.n_stages; ++st) {
-      const int r = plan.radix[st];
-      blk /= r;
-      pos += (rem % r) * blk;
-      rem /= r;
+  float* mag;
+  if (direct) {
+    float* xs = reinterpret_cast<float*>(smem_raw);
+    mag = xs + N;
+    for (int i = tid; i < N; i += nthr) xs[i] = __ldg(x + i);
+    __syncthreads();
+    for (int k = tid; k < nbins; k += nthr) {
+      double re = 0.0, im = 0.0;
+      int idx = 0;  // (n * k) mod N, kept exact
+      for (int n = 0; n < N; ++n) {
+        float sn, cs;
+        sincospif(-2.0f * (float)idx / (float)N, &sn, &cs);
+        re += (double)xs[n] * (double)cs;
+        im += (double)xs[n] * (double)sn;
+        idx += k;
+        if (idx >= N) idx -= N;
+      }
+      mag[k] = (float)sqrt(re * re + im * im);
     }
-    z[pos] = even ? make_float2(__ldg(x + 2 * n), __ldg(x + 2 * n + 1)) : make_float2(__ldg(x + n), 0.f);
-  }
-  __syncthreads();
+    __syncthreads();
+  } else {
+    // digit-reversed load: position of input n under mixed-radix DIT (first radix = outermost)
+    for (int n = tid; n < M; n += nthr) {
+      int rem = n, pos = 0, blk = M;
+      for (int st = 0; st < plan.n_stages; ++st) {
+        const int r = plan.radix[st];
+        blk /= r;
+        pos += (rem % r) * blk;
+        rem /= r;
+      }
+      z[pos] = even ? make_float2(__ldg(x + 2 * n), __ldg(x + 2 * n + 1)) : make_float2(__ldg(x + n), 0.f);
+    }
+    __syncthreads();
 
-  // --- in-place decimation-in-time passes, innermost (last radix) first
-  int Lprev = 1;
-  for (int st = plan.n_stages - 1; st >= 0; --st) {
-    const int r = plan.radix[st];
-    const int L = Lprev * r;
-    const int nb = M / r;  // butterflies this pass
-    for (int t = tid; t < nb; t += nthr) {
-      const int k0 = t % Lprev;
-      const int base = (t / Lprev) * L + k0;
-      if (r == 4) butterfly_fixed<4>(z, base, Lprev, k0, L);
-      else if (r == 2) butterfly_fixed<2>(z, base, Lprev, k0, L);
-      else if (r == 5) butterfly_fixed<5>(z, base, Lprev, k0, L);
-      else if (r == 3) butterfly_fixed<3>(z, base, Lprev, k0, L);
-      else butterfly_generic(z, base, Lprev, k0, L, r);
+    // in-place decimation-in-time passes, innermost (last radix) first
+    int Lprev = 1;
+    for (int st = plan.n_stages - 1; st >= 0; --st) {
+      const int r = plan.radix[st];
+      const int L = Lprev * r;
+      const int nb = M / r;  // butterflies this pass
+      for (int t = tid; t < nb; t += nthr) {
+        const int k0 = t % Lprev;
+        const int base = (t / Lprev) * L + k0;
+        if (r == 4) butterfly_fixed<4>(z, base, Lprev, k0, L);
+        else if (r == 2) butterfly_fixed<2>(z, base, Lprev, k0, L);
+        else if (r == 5) butterfly_fixed<5>(z, base, Lprev, k0, L);
+        else if (r == 3) butterfly_fixed<3>(z, base, Lprev, k0, L);
+        else butterfly_generic(z, base, Lprev, k0, L, r);
+      }
+      Lprev = L;
+      __syncthreads();
     }
-    Lprev = L;
+
+    // magnitudes of the N/2+1 real-FFT bins, stored over z: every thread first computes its bins
+    // into registers (strided ownership), then all store after a barrier.
+    mag = reinterpret_cast<float*>(smem_raw);
+    float vals[64];
+    int cnt = 0;
+    for (int k = tid; k < nbins; k += nthr) {
+      float2 X;
+      if (even) {
+        const float2 zk = z[k % M];
+        float2 zm = z[(M - k) % M];
+        zm.y = -zm.y;
+        const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
+        const float2 D = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
+        const float2 O = make_float2(D.y, -D.x);
+        float sn, cs;
+        sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
+        X = cadd(E, cmul(make_float2(cs, sn), O));
+      } else {
+        X = z[k];
+      }
+      vals[cnt++] = sqrtf(X.x * X.x + X.y * X.y);
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int k = tid; k < nbins; k += nthr) mag[k] = vals[cnt++];
     __syncthreads();
   }
-
-  // --- magnitudes of the N/2+1 real-FFT bins; stored in place as float (bin k -> zf[k])
-  const int nbins = N / 2 + 1;
-  float* mag = reinterpret_cast<float*>(smem_raw);  // overwrites z progressively: staged below
-  // Each bin k needs Z[k] and Z[M-k]; compute into registers first (strided ownership), sync, store.
-  // Ownership: thread handles k = tid, tid + nthr, ...; at most ceil(nbins / nthr) values.
-  float vals[64];
-  int cnt = 0;
-  for (int k = tid; k < nbins; k += nthr) {
-    float2 X;
-    if (even) {
-      const float2 zk = z[k % M];
-      float2 zm = z[(M - k) % M];
-      zm.y = -zm.y;
-      const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
-      const float2 D = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
-      const float2 O = make_float2(D.y, -D.x);
-      float sn, cs;
-      sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
-      X = cadd(E, cmul(make_float2(cs, sn), O));
-    } else {
-      X = z[k];
-    }
-    vals[cnt++] = sqrtf(X.x * X.x + X.y * X.y);
-  }
-  __syncthreads();
-  cnt = 0;
-  for (int k = tid; k < nbins; k += nthr) mag[k] = vals[cnt++];
-  __syncthreads();
 
   // --- spectral sums in double: S0 = sum mag, S1 = sum f mag
   const double df = (double)a.sample_rate / (double)N;

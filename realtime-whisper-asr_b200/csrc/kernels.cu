@@ -1,0 +1,458 @@
+// Small memory-bound kernels around the GEMMs: LayerNorm, embeddings, KV-cache scatter, Whisper
+// logit rules + log-softmax + top-k, token probabilities, and the word-timing chain
+// (normalise -> median filter -> head mean -> DTW).
+#include "kernels.h"
+
+#include <float.h>
+
+namespace b200w {
+
+// ------------------------------------------------------------------------------- LayerNorm
+// one warp per row; x fp32 (optionally gathered through row_idx) -> y bf16.  d % 128 == 0, d <= 1280
+__global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict__ x,
+                                                        const int* __restrict__ row_idx,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta,
+                                                        bf16* __restrict__ y, int rows, int d) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long long src = row_idx ? row_idx[row] : row;
+  const float4* xp = reinterpret_cast<const float4*>(x + src * d);
+  const int nv = d >> 7;  // float4 per lane
+  float4 v[10];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    if (i < nv) {
+      v[i] = xp[lane + 32 * i];
+      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)d;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      sq += a * a + b * b + c * c + e * e;
+    }
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)d + 1e-5f);
+  const float4* gp = reinterpret_cast<const float4*>(gamma);
+  const float4* bp = reinterpret_cast<const float4*>(beta);
+  uint2* yp = reinterpret_cast<uint2*>(y + (long long)row * d);
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    if (i < nv) {
+      const float4 g = __ldg(gp + lane + 32 * i), b = __ldg(bp + lane + 32 * i);
+      __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + b.x,
+                                                (v[i].y - mean) * rstd * g.y + b.y);
+      __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + b.z,
+                                                (v[i].w - mean) * rstd * g.w + b.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      yp[lane + 32 * i] = u;
+    }
+}
+
+void layernorm(const float* x, const int* row_idx, const float* gamma, const float* beta, bf16* y,
+               int rows, int d, cudaStream_t stream) {
+  if (rows <= 0) return;
+  B200W_REQUIRE(d % 128 == 0 && d <= 1280, "LayerNorm width must be a multiple of 128, <= 1280");
+  layernorm_kernel<<<cdiv(rows, 4), 128, 0, stream>>>(x, row_idx, gamma, beta, y, rows, d);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------- embeddings
+__global__ void embed_kernel(const int* __restrict__ tok, const int* __restrict__ pos,
+                             const bf16* __restrict__ tok_emb, const float* __restrict__ pos_emb,
+                             float* __restrict__ x, int d) {
+  const int n = blockIdx.x;
+  const bf16* te = tok_emb + (long long)tok[n] * d;
+  const float* pe = pos_emb + (long long)pos[n] * d;
+  for (int c = threadIdx.x * 2; c < d; c += blockDim.x * 2) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(te + c));
+    const float2 p = *reinterpret_cast<const float2*>(pe + c);
+    *reinterpret_cast<float2*>(x + (long long)n * d + c) = make_float2(t.x + p.x, t.y + p.y);
+  }
+}
+
+void embed_tokens(const int* tok, const int* pos, const bf16* tok_emb, const float* pos_emb, float* x,
+                  int n, int d, cudaStream_t stream) {
+  if (n <= 0) return;
+  embed_kernel<<<n, 128, 0, stream>>>(tok, pos, tok_emb, pos_emb, x, d);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------- KV scatter
+// qkv bf16 [n][3d] -> kpool[slot[n]][d], vpool[slot[n]][d]
+__global__ void kv_scatter_kernel(const bf16* __restrict__ qkv, const int* __restrict__ slot,
+                                  bf16* __restrict__ kpool, bf16* __restrict__ vpool, int d) {
+  const int n = blockIdx.x;
+  const long long s = slot[n];
+  const uint4* src = reinterpret_cast<const uint4*>(qkv + (long long)n * 3 * d + d);
+  uint4* kd = reinterpret_cast<uint4*>(kpool + s * d);
+  uint4* vd = reinterpret_cast<uint4*>(vpool + s * d);
+  const int nv = d >> 3;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    kd[i] = src[i];
+    vd[i] = src[nv + i];
+  }
+}
+
+void kv_scatter(const bf16* qkv, const int* slot, bf16* kpool, bf16* vpool, int n, int d,
+                cudaStream_t stream) {
+  if (n <= 0) return;
+  kv_scatter_kernel<<<n, 128, 0, stream>>>(qkv, slot, kpool, vpool, d);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------- sampling
+__device__ __forceinline__ float block_reduce_max(float v, float* s) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, s[w]);
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* s) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += s[w];
+  return r;
+}
+
+__device__ __forceinline__ bool token_masked(int v, const SampleParams& p, const int4 st,
+                                             const unsigned char* mask) {
+  // st.x flags, st.y ts_lo
+  if (mask[v] & 1) return true;                            // static suppress list
+  if ((st.x & SF_FIRST) && (mask[v] & 2)) return true;     // suppress_blank at the first position
+  if (!(st.x & SF_RULES)) return false;
+  if (v == p.no_timestamps) return true;
+  if (v >= p.timestamp_begin) {
+    if (st.x & SF_SUP_ALL_TS) return true;
+    if (v < st.y) return true;                             // timestamps must not decrease
+    if ((st.x & SF_FIRST) && v > p.timestamp_begin + p.max_initial_ts) return true;
+  } else {
+    if ((st.x & SF_FIRST)) return true;                    // first token must be a timestamp
+    if ((st.x & SF_SUP_TEXT) && v < p.eot) return true;    // after a lone timestamp: ts or EOT
+  }
+  return false;
+}
+
+// One CTA per row: masked log-softmax with Whisper's timestamp rules, then top-k.
+__global__ void __launch_bounds__(256) sample_kernel(const SampleParams p) {
+  __shared__ float s_red[8];
+  __shared__ float s_cv[256];
+  __shared__ int s_ci[256];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const float* lg = p.logits + (long long)row * p.ld;
+  const int4 st = p.state[row];
+  const int V = p.n_vocab;
+
+  float mx = -INFINITY, mx_text = -INFINITY;
+  for (int v = tid; v < V; v += 256) {
+    if (token_masked(v, p, st, p.mask)) continue;
+    const float x = lg[v];
+    mx = fmaxf(mx, x);
+    if (v < p.timestamp_begin) mx_text = fmaxf(mx_text, x);
+  }
+  mx = block_reduce_max(mx, s_red);
+  mx_text = block_reduce_max(mx_text, s_red);
+  float sum_all = 0.f, sum_ts = 0.f;
+  for (int v = tid; v < V; v += 256) {
+    if (token_masked(v, p, st, p.mask)) continue;
+    const float e = __expf(lg[v] - mx);
+    sum_all += e;
+    if (v >= p.timestamp_begin) sum_ts += e;
+  }
+  sum_all = block_reduce_sum(sum_all, s_red);
+  sum_ts = block_reduce_sum(sum_ts, s_red);
+  float lse = mx + logf(sum_all);
+  bool ts_only = false;
+  if ((st.x & SF_RULES) && sum_ts > 0.f) {
+    // if the total timestamp mass beats every single text token, force a timestamp
+    const float ts_logprob = mx + logf(sum_ts) - lse;
+    const float text_logprob = mx_text - lse;
+    if (ts_logprob > text_logprob) {
+      ts_only = true;
+      lse = mx + logf(sum_ts);
+    }
+  }
+
+  // per-thread top-k (k <= MAX_TOPK), kept sorted descending; ties -> lower token id first
+  float bv[MAX_TOPK];
+  int bi[MAX_TOPK];
+#pragma unroll
+  for (int j = 0; j < MAX_TOPK; ++j) { bv[j] = -INFINITY; bi[j] = 0x7fffffff; }
+  const int k = p.k;
+  for (int v = tid; v < V; v += 256) {
+    if (token_masked(v, p, st, p.mask)) continue;
+    if (ts_only && v < p.timestamp_begin) continue;
+    const float x = lg[v] - lse;
+    if (x > bv[k - 1]) {
+      int j = k - 1;
+      while (j > 0 && x > bv[j - 1]) { bv[j] = bv[j - 1]; bi[j] = bi[j - 1]; --j; }
+      bv[j] = x;
+      bi[j] = v;
+    }
+  }
+  int head = 0;
+  for (int r = 0; r < k; ++r) {
+    // block argmax over every thread's current head; ties -> lower id
+    float cv = head < k ? bv[head] : -INFINITY;
+    int ci = head < k ? bi[head] : 0x7fffffff;
+    s_cv[tid] = cv;
+    s_ci[tid] = ci;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o) {
+        const float ov = s_cv[tid + o];
+        const int oi = s_ci[tid + o];
+        if (ov > s_cv[tid] || (ov == s_cv[tid] && oi < s_ci[tid])) { s_cv[tid] = ov; s_ci[tid] = oi; }
+      }
+      __syncthreads();
+    }
+    const float wv = s_cv[0];
+    const int wi = s_ci[0];
+    if (tid == 0) {
+      p.out_ids[row * k + r] = wi;
+      p.out_logprobs[row * k + r] = wv;
+    }
+    if (head < k && bi[head] == wi && wi != 0x7fffffff) ++head;
+    __syncthreads();
+  }
+}
+
+void sample_topk(const SampleParams& p, int rows, cudaStream_t stream) {
+  if (rows <= 0) return;
+  B200W_REQUIRE(p.k >= 1 && p.k <= MAX_TOPK, "top-k out of range");
+  sample_kernel<<<rows, 256, 0, stream>>>(p);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+// softmax probability of given tokens over raw logits rows.  One CTA per (row).
+// mode 0: out[row] = softmax(logits[row])[tok[row]]
+// mode 1: out[row][j] = softmax restricted to ids[0..n_ids) (language detection)
+__global__ void __launch_bounds__(256) token_prob_kernel(const float* __restrict__ logits, int ld,
+                                                         int n_vocab, const int* __restrict__ rows,
+                                                         const int* __restrict__ tok,
+                                                         const int* __restrict__ ids, int n_ids,
+                                                         float* __restrict__ out) {
+  __shared__ float s_red[8];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* lg = logits + (long long)(rows ? rows[r] : r) * ld;
+  if (ids == nullptr) {
+    float mx = -INFINITY;
+    for (int v = tid; v < n_vocab; v += 256) mx = fmaxf(mx, lg[v]);
+    mx = block_reduce_max(mx, s_red);
+    float sum = 0.f;
+    for (int v = tid; v < n_vocab; v += 256) sum += __expf(lg[v] - mx);
+    sum = block_reduce_sum(sum, s_red);
+    if (tid == 0) out[r] = __expf(lg[tok[r]] - mx) / sum;
+  } else {
+    float mx = -INFINITY;
+    for (int j = tid; j < n_ids; j += 256) mx = fmaxf(mx, lg[ids[j]]);
+    mx = block_reduce_max(mx, s_red);
+    float sum = 0.f;
+    for (int j = tid; j < n_ids; j += 256) sum += __expf(lg[ids[j]] - mx);
+    sum = block_reduce_sum(sum, s_red);
+    for (int j = tid; j < n_ids; j += 256) out[(long long)r * n_ids + j] = __expf(lg[ids[j]] - mx) / sum;
+  }
+}
+
+void token_probs(const float* logits, int ld, int n_vocab, const int* rows, const int* tok,
+                 const int* ids, int n_ids, float* out, int n_rows, cudaStream_t stream) {
+  if (n_rows <= 0) return;
+  token_prob_kernel<<<n_rows, 256, 0, stream>>>(logits, ld, n_vocab, rows, tok, ids, n_ids, out);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------- word timing
+// w: [n_align][n_q][stride] attention probabilities; sequence b owns query rows [q0, q0 + n_tok)
+// and frames [0, nf).  Standardise every (head, frame) column over the tokens (population std).
+__global__ void align_normalize_kernel(float* __restrict__ w, int n_q, int stride,
+                                       const int* __restrict__ seq_q0, const int* __restrict__ seq_ntok,
+                                       const int* __restrict__ seq_nf) {
+  const int b = blockIdx.z, a = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nf = seq_nf[b], nt = seq_ntok[b];
+  if (f >= nf) return;
+  float* col = w + ((long long)a * n_q + seq_q0[b]) * stride + f;
+  float mean = 0.f;
+  for (int t = 0; t < nt; ++t) mean += col[(long long)t * stride];
+  mean /= (float)nt;
+  float var = 0.f;
+  for (int t = 0; t < nt; ++t) {
+    const float dlt = col[(long long)t * stride] - mean;
+    var += dlt * dlt;
+  }
+  const float stdv = sqrtf(var / (float)nt);
+  for (int t = 0; t < nt; ++t) col[(long long)t * stride] = (col[(long long)t * stride] - mean) / stdv;
+}
+
+// matrix[b][t][f] = mean over heads of median_{width}(w[a][t][f-h..f+h]) (reflect padding)
+__global__ void align_median_mean_kernel(const float* __restrict__ w, int n_align, int n_q, int stride,
+                                         const int* __restrict__ seq_q0,
+                                         const int* __restrict__ seq_ntok,
+                                         const int* __restrict__ seq_nf, int width,
+                                         float* __restrict__ matrix, int mat_stride) {
+  const int b = blockIdx.z, t = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nf = seq_nf[b];
+  if (t >= seq_ntok[b] || f >= nf) return;
+  const int half = width / 2;
+  float acc = 0.f;
+  for (int a = 0; a < n_align; ++a) {
+    const float* row = w + ((long long)a * n_q + seq_q0[b] + t) * stride;
+    float val;
+    if (nf <= half || width <= 1) {
+      val = row[f];  // too short to filter (OpenAI/CT2 skip the filter)
+    } else {
+      float win[9];
+      for (int j = 0; j < width; ++j) {
+        int g = f - half + j;
+        if (g < 0) g = -g;
+        if (g >= nf) g = 2 * (nf - 1) - g;
+        win[j] = row[g];
+      }
+      for (int i = 1; i < width; ++i) {  // insertion sort
+        const float x = win[i];
+        int j = i - 1;
+        while (j >= 0 && win[j] > x) { win[j + 1] = win[j]; --j; }
+        win[j + 1] = x;
+      }
+      val = win[half];
+    }
+    acc += val;
+  }
+  matrix[((long long)seq_q0[b] + t) * mat_stride + f] = acc / (float)n_align;
+}
+
+// DTW over cost = -matrix[rows r0 .. r0+N) x [0, M), one CTA per sequence (anti-diagonal wavefront).
+// trace: int8 [(N+1)][(M+1)] scratch per sequence.  path: (text, time) pairs in forward order.
+__global__ void __launch_bounds__(512) dtw_kernel(const float* __restrict__ matrix, int mat_stride,
+                                                  const int* __restrict__ seq_q0,
+                                                  const int* __restrict__ seq_ntok,
+                                                  const int* __restrict__ seq_nf, int row_lo,
+                                                  int row_hi_trim, signed char* __restrict__ trace_all,
+                                                  long long trace_stride, int* __restrict__ path,
+                                                  int max_path, int* __restrict__ path_len) {
+  extern __shared__ float s_diag[];  // 3 x (Nmax + 1)
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int N = seq_ntok[b] - row_lo - row_hi_trim;  // text rows
+  const int M = seq_nf[b];
+  int* out = path + (long long)b * max_path * 2;
+  if (N <= 0 || M <= 0) {
+    if (tid == 0) path_len[b] = 0;
+    return;
+  }
+  const float* x = matrix + ((long long)seq_q0[b] + row_lo) * mat_stride;
+  signed char* trace = trace_all + (long long)b * trace_stride;
+  const int W = M + 1;
+  const int NP = N + 1;
+  float* d0 = s_diag;            // diagonal d-2
+  float* d1 = s_diag + NP;       // diagonal d-1
+  float* d2 = s_diag + 2 * NP;   // diagonal d   (indexed by i)
+  for (int i = tid; i < NP; i += blockDim.x) { d0[i] = INFINITY; d1[i] = INFINITY; d2[i] = INFINITY; }
+  __syncthreads();
+  if (tid == 0) d0[0] = 0.f;  // cost[0][0] lives on diagonal 0
+  __syncthreads();
+  // diagonal 1 holds cost[0][1] and cost[1][0] = inf (already)
+  for (int d = 2; d <= N + M; ++d) {
+    const int ilo = max(1, d - M), ihi = min(N, d - 1);
+    for (int i = ilo + tid; i <= ihi; i += blockDim.x) {
+      const int j = d - i;
+      const float c0 = d0[i - 1];  // cost[i-1][j-1]
+      const float c1 = d1[i - 1];  // cost[i-1][j]
+      const float c2 = d1[i];      // cost[i][j-1]
+      float c;
+      signed char t;
+      if (c0 < c1 && c0 < c2) { c = c0; t = 0; }
+      else if (c1 < c0 && c1 < c2) { c = c1; t = 1; }
+      else { c = c2; t = 2; }
+      d2[i] = -x[(long long)(i - 1) * mat_stride + (j - 1)] + c;
+      trace[(long long)i * W + j] = t;
+    }
+    __syncthreads();
+    // rotate: entries outside the active range of the new d1/d0 must read as inf
+    float* tmp = d0; d0 = d1; d1 = d2; d2 = tmp;
+    for (int i = tid; i < NP; i += blockDim.x) d2[i] = INFINITY;
+    if (tid == 0 && d == 2) { /* cost[0][*] = inf for * > 0 */ d0[0] = INFINITY; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int i = N, j = M, n = 0;
+    // backtrace; written reversed into the tail of the buffer, then shifted to the front
+    int* tmpbuf = out;
+    while ((i > 0 || j > 0) && n < max_path) {
+      tmpbuf[2 * n] = i - 1;
+      tmpbuf[2 * n + 1] = j - 1;
+      ++n;
+      signed char t;
+      if (i == 0) t = 2; else if (j == 0) t = 1; else t = trace[(long long)i * W + j];
+      if (t == 0) { --i; --j; } else if (t == 1) { --i; } else { --j; }
+    }
+    for (int a = 0, z = n - 1; a < z; ++a, --z) {
+      const int t0 = tmpbuf[2 * a], t1 = tmpbuf[2 * a + 1];
+      tmpbuf[2 * a] = tmpbuf[2 * z]; tmpbuf[2 * a + 1] = tmpbuf[2 * z + 1];
+      tmpbuf[2 * z] = t0; tmpbuf[2 * z + 1] = t1;
+    }
+    path_len[b] = n;
+  }
+}
+
+void align_postprocess(float* weights, int n_align, int n_q, int stride, const int* seq_q0,
+                       const int* seq_ntok, const int* seq_nf, int n_seq, int max_ntok, int max_nf,
+                       int median_width, float* matrix, int row_lo, int row_hi_trim,
+                       signed char* trace, long long trace_stride, int* path, int max_path,
+                       int* path_len, cudaStream_t stream) {
+  if (n_seq <= 0) return;
+  B200W_REQUIRE(median_width <= 9 && (median_width & 1) == 1, "median width must be odd and <= 9");
+  align_normalize_kernel<<<dim3(cdiv(max_nf, 128), n_align, n_seq), 128, 0, stream>>>(
+      weights, n_q, stride, seq_q0, seq_ntok, seq_nf);
+  B200W_COUNT_LAUNCH();
+  align_median_mean_kernel<<<dim3(cdiv(max_nf, 128), max_ntok, n_seq), 128, 0, stream>>>(
+      weights, n_align, n_q, stride, seq_q0, seq_ntok, seq_nf, median_width, matrix, stride);
+  B200W_COUNT_LAUNCH();
+  const size_t smem = 3 * (size_t)(max_ntok + 1) * sizeof(float);
+  dtw_kernel<<<n_seq, 512, smem, stream>>>(matrix, stride, seq_q0, seq_ntok, seq_nf, row_lo,
+                                           row_hi_trim, trace, trace_stride, path, max_path, path_len);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------- page tables
+// Beam fork: new[row[i]][0:pos[i]] = old[parent[i]][0:pos[i]]; new[row[i]][pos[i]] = slot[i].
+__global__ void fork_tables_kernel(const int* __restrict__ old_t, const int* __restrict__ parent,
+                                   const int* __restrict__ row, const int* __restrict__ pos,
+                                   const int* __restrict__ slot, int* __restrict__ new_t, int stride) {
+  const int i = blockIdx.x;
+  const int* s = old_t + (long long)parent[i] * stride;
+  int* d = new_t + (long long)row[i] * stride;
+  const int len = pos[i];
+  for (int j = threadIdx.x; j < len; j += blockDim.x) d[j] = s[j];
+  if (threadIdx.x == 0) d[len] = slot[i];
+}
+
+void gather_fork_tables(const int* old_t, const int* parent, const int* row, const int* pos,
+                        const int* slot, int* new_t, int n, int stride, cudaStream_t stream) {
+  if (n <= 0) return;
+  fork_tables_kernel<<<n, 128, 0, stream>>>(old_t, parent, row, pos, slot, new_t, stride);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+}  // namespace b200w

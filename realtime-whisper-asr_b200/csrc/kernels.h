@@ -1,0 +1,47 @@
+// Launchers for the small memory-bound kernels (kernels.cu).  All pointers are device pointers.
+#pragma once
+#include "common.h"
+
+namespace b200w {
+
+void layernorm(const float* x, const int* row_idx, const float* gamma, const float* beta, bf16* y,
+               int rows, int d, cudaStream_t stream);
+void embed_tokens(const int* tok, const int* pos, const bf16* tok_emb, const float* pos_emb, float* x,
+                  int n, int d, cudaStream_t stream);
+void kv_scatter(const bf16* qkv, const int* slot, bf16* kpool, bf16* vpool, int n, int d,
+                cudaStream_t stream);
+
+// per-row sampling state flags (state[row].x); state[row].y = lowest admissible timestamp id
+enum : int {
+  SF_RULES = 1,       // apply Whisper timestamp rules
+  SF_FIRST = 2,       // first sampled position
+  SF_SUP_ALL_TS = 4,  // last two tokens were timestamps: no timestamp may follow
+  SF_SUP_TEXT = 8,    // last token was an unpaired timestamp: only timestamps / EOT may follow
+};
+static constexpr int MAX_TOPK = 16;
+
+struct SampleParams {
+  const float* logits;  // [rows][ld]
+  int ld, n_vocab;
+  const unsigned char* mask;  // [n_vocab] bit0: always suppressed, bit1: suppressed at first position
+  const int4* state;          // [rows]
+  int eot, no_timestamps, timestamp_begin, max_initial_ts;
+  int k;
+  int* out_ids;         // [rows][k]
+  float* out_logprobs;  // [rows][k]
+};
+void sample_topk(const SampleParams& p, int rows, cudaStream_t stream);
+
+void token_probs(const float* logits, int ld, int n_vocab, const int* rows, const int* tok,
+                 const int* ids, int n_ids, float* out, int n_rows, cudaStream_t stream);
+
+void align_postprocess(float* weights, int n_align, int n_q, int stride, const int* seq_q0,
+                       const int* seq_ntok, const int* seq_nf, int n_seq, int max_ntok, int max_nf,
+                       int median_width, float* matrix, int row_lo, int row_hi_trim,
+                       signed char* trace, long long trace_stride, int* path, int max_path,
+                       int* path_len, cudaStream_t stream);
+
+void gather_fork_tables(const int* old_t, const int* parent, const int* row, const int* pos,
+                        const int* slot, int* new_t, int n, int stride, cudaStream_t stream);
+
+}  // namespace b200w

@@ -104,6 +104,31 @@ def pack_windows(mel: MelBatch, win_stream: Sequence[int], seeks: Sequence[int])
     return windows
 
 
+def _dedup_points(n: int) -> int:
+    """Shared-memory footprint of a chunk in 8-byte units (mirrors dedup_features_kernel)."""
+    m = n // 2 if n % 2 == 0 else n
+    r = m
+    for p in (2, 3, 5):
+        while r > 1 and r % p == 0:
+            r //= p
+    p = 7
+    smooth = True
+    while r > 1:
+        if r % p == 0:
+            if p > 64:
+                smooth = False
+                break
+            r //= p
+        else:
+            p += 2
+            if p > 64 and r > 1:
+                smooth = False
+                break
+    if smooth:
+        return max(m, 1)
+    return (4 * (n + n // 2 + 1) + 7) // 8  # direct DFT: samples + magnitudes as fp32
+
+
 def dedup_features(audio_dev: torch.Tensor, offsets: np.ndarray, sample_rate: int = SAMPLE_RATE,
                    return_raw: bool = False):
     """AudioDeduplicator._extract_features for every chunk; returns fp32 [n_chunks, 5] on device."""
@@ -114,8 +139,10 @@ def dedup_features(audio_dev: torch.Tensor, offsets: np.ndarray, sample_rate: in
     if n == 0:
         z = torch.zeros((0, 5), dtype=torch.float32, device=device)
         return (z, z) if return_raw else z
-    pts = np.where(lens % 2 == 0, lens // 2, lens)
-    max_points = int(pts.max())
+    max_points = max(_dedup_points(int(n_)) for n_ in set(lens.tolist()))
+    if max_points > 27648:
+        raise _lib.B200WError("dedup chunk too long for the shared-memory DFT "
+                              "(N <= 55296 samples even, 27648 odd)")
     off_dev = torch.from_numpy(np.asarray(offsets, dtype=np.int64)).to(device, non_blocking=True)
     out = torch.empty((n, 5), dtype=torch.float32, device=device)
     raw = torch.empty((n, 5), dtype=torch.float32, device=device) if return_raw else None

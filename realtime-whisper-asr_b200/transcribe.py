@@ -1,0 +1,527 @@
+"""``B200WhisperModel``: the object the reference's backend wrapper holds as ``self.model``.
+
+Shaped like ``faster_whisper.WhisperModel`` for exactly the surface the reference uses:
+``create_custom_faster_whisper_asr`` builds it in ``load_model`` and calls
+``self.model.transcribe(audio, language=, initial_prompt=, beam_size=, temperature=,
+word_timestamps=True, condition_on_previous_text=True, **kw) -> (segments, info)``
+(/root/reference/asr_components.py:232-289); it then reads ``Segment.words[*].{start,end,word}``,
+``Segment.end`` and (upstream ``FasterWhisperASR.ts_words``) ``Segment.no_speech_prob``.
+
+The pipeline below restates faster-whisper's ``transcribe`` / ``generate_segments`` (SURVEY.md
+A.2): features -> 30 s windows from ``seek`` -> prompt -> generate -> no-speech skip -> split by
+timestamp tokens -> word timestamps (align + DTW, duration heuristics, punctuation merge) ->
+``Segment`` / ``Word``.  All tensor work runs in libb200whisper.so; what stays here is token-list
+and string bookkeeping.  ``transcribe_batch`` runs many independent streams through the same
+steps with one encoder / decoder / align launch per round (streams are the natural shard).
+"""
+from __future__ import annotations
+
+import itertools
+import zlib
+from dataclasses import dataclass, field
+from typing import Iterable, List, NamedTuple, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib, frontend
+from .engine import DecodeOptions, WhisperEngine
+from .tokenizer import Tokenizer
+from .weights import (ALIGNMENT_HEADS, MODEL_DIMS, ModelDims, default_alignment_heads, pack_for_engine,
+                      synthetic_state_dict)
+
+SAMPLE_RATE = 16000
+HOP = 160
+N_FRAMES = 3000
+FRAMES_PER_SECOND = 100
+TOKENS_PER_SECOND = 50
+TIME_PRECISION = 0.02
+INPUT_STRIDE = 2
+MAX_LENGTH = 448
+
+
+class Word(NamedTuple):
+    start: float
+    end: float
+    word: str
+    probability: float
+
+
+class Segment(NamedTuple):
+    id: int
+    seek: int
+    start: float
+    end: float
+    text: str
+    tokens: List[int]
+    avg_logprob: float
+    compression_ratio: float
+    no_speech_prob: float
+    words: Optional[List[Word]]
+    temperature: float = 0.0
+
+
+class TranscriptionOptions(NamedTuple):
+    beam_size: int
+    best_of: int
+    patience: float
+    length_penalty: float
+    repetition_penalty: float
+    no_repeat_ngram_size: int
+    log_prob_threshold: Optional[float]
+    no_speech_threshold: Optional[float]
+    compression_ratio_threshold: Optional[float]
+    condition_on_previous_text: bool
+    prompt_reset_on_temperature: float
+    temperatures: List[float]
+    initial_prompt: Optional[Union[str, Iterable[int]]]
+    prefix: Optional[str]
+    suppress_blank: bool
+    suppress_tokens: Optional[List[int]]
+    without_timestamps: bool
+    max_initial_timestamp: float
+    word_timestamps: bool
+    prepend_punctuations: str
+    append_punctuations: str
+    max_new_tokens: Optional[int]
+
+
+class TranscriptionInfo(NamedTuple):
+    language: str
+    language_probability: float
+    duration: float
+    duration_after_vad: float
+    all_language_probs: Optional[List[Tuple[str, float]]]
+    transcription_options: TranscriptionOptions
+    vad_options: None = None
+
+
+@dataclass
+class _Stream:
+    """Per-stream state of the seek loop (faster-whisper generate_segments)."""
+    sid: int
+    content_frames: int
+    tokenizer: Tokenizer
+    options: TranscriptionOptions
+    seek: int = 0
+    idx: int = 0
+    all_tokens: List[int] = field(default_factory=list)
+    prompt_reset_since: int = 0
+    last_speech_timestamp: float = 0.0
+    segments: List[Segment] = field(default_factory=list)
+    # per-round scratch
+    segment_size: int = 0
+    time_offset: float = 0.0
+    prompt: List[int] = field(default_factory=list)
+
+
+def get_compression_ratio(text: str) -> float:
+    b = text.encode("utf-8")
+    return len(b) / len(zlib.compress(b))
+
+
+def get_prompt(tokenizer: Tokenizer, previous_tokens: List[int], without_timestamps: bool = False,
+               prefix: Optional[str] = None) -> List[int]:
+    prompt: List[int] = []
+    if previous_tokens:
+        prompt.append(tokenizer.sot_prev)
+        prompt.extend(previous_tokens[-(MAX_LENGTH // 2 - 1):])
+    prompt.extend(tokenizer.sot_sequence)
+    if without_timestamps:
+        prompt.append(tokenizer.no_timestamps)
+    if prefix:
+        prefix_tokens = tokenizer.encode(" " + prefix.strip())
+        if len(prefix_tokens) >= MAX_LENGTH // 2:
+            prefix_tokens = prefix_tokens[: MAX_LENGTH // 2 - 1]
+        if not without_timestamps:
+            prompt.append(tokenizer.timestamp_begin)
+        prompt.extend(prefix_tokens)
+    return prompt
+
+
+def split_segments_by_timestamps(tokenizer: Tokenizer, tokens: List[int], time_offset: float, segment_size: int,
+                                 segment_duration: float, seek: int):
+    tb = tokenizer.timestamp_begin
+    current_segments = []
+    single_timestamp_ending = len(tokens) >= 2 and tokens[-2] < tb <= tokens[-1]
+    consecutive = [i for i in range(len(tokens)) if i > 0 and tokens[i] >= tb and tokens[i - 1] >= tb]
+    if consecutive:
+        slices = list(consecutive)
+        if single_timestamp_ending:
+            slices.append(len(tokens))
+        last_slice = 0
+        for current_slice in slices:
+            sliced = tokens[last_slice:current_slice]
+            start_pos = sliced[0] - tb
+            end_pos = sliced[-1] - tb
+            current_segments.append(dict(seek=seek, start=time_offset + start_pos * TIME_PRECISION,
+                                         end=time_offset + end_pos * TIME_PRECISION, tokens=sliced))
+            last_slice = current_slice
+        if single_timestamp_ending:
+            seek += segment_size  # no speech after the last timestamp
+        else:
+            seek += (tokens[last_slice - 1] - tb) * INPUT_STRIDE  # resume at the last timestamp
+    else:
+        duration = segment_duration
+        timestamps = [t for t in tokens if t >= tb]
+        if timestamps and timestamps[-1] != tb:
+            duration = (timestamps[-1] - tb) * TIME_PRECISION
+        current_segments.append(dict(seek=seek, start=time_offset, end=time_offset + duration, tokens=tokens))
+        seek += segment_size
+    return current_segments, seek, single_timestamp_ending
+
+
+def merge_punctuations(alignment: List[dict], prepended: str, appended: str) -> None:
+    i, j = len(alignment) - 2, len(alignment) - 1
+    while i >= 0:
+        previous, following = alignment[i], alignment[j]
+        if previous["word"].startswith(" ") and previous["word"].strip() in prepended:
+            following["word"] = previous["word"] + following["word"]
+            following["tokens"] = previous["tokens"] + following["tokens"]
+            previous["word"] = ""
+            previous["tokens"] = []
+        else:
+            j = i
+        i -= 1
+    i, j = 0, 1
+    while j < len(alignment):
+        previous, following = alignment[i], alignment[j]
+        if not previous["word"].endswith(" ") and following["word"] in appended:
+            previous["word"] = previous["word"] + following["word"]
+            previous["tokens"] = previous["tokens"] + following["tokens"]
+            following["word"] = ""
+            following["tokens"] = []
+        else:
+            i = j
+        j += 1
+
+
+def words_from_alignment(tokenizer: Tokenizer, text_tokens: List[int], text_indices: np.ndarray,
+                         time_indices: np.ndarray, text_token_probs: np.ndarray) -> List[dict]:
+    """faster-whisper find_alignment, after the device returned the DTW path."""
+    words, word_tokens = tokenizer.split_to_word_tokens(text_tokens + [tokenizer.eot])
+    if len(word_tokens) <= 1:
+        return []
+    word_boundaries = np.pad(np.cumsum([len(t) for t in word_tokens[:-1]]), (1, 0))
+    if len(word_boundaries) <= 1 or len(text_indices) == 0:
+        return []
+    jumps = np.pad(np.diff(text_indices), (1, 0), constant_values=1).astype(bool)
+    jump_times = time_indices[jumps] / TOKENS_PER_SECOND
+    start_times = jump_times[word_boundaries[:-1]]
+    end_times = jump_times[word_boundaries[1:]]
+    probs = [float(np.mean(text_token_probs[i:j])) for i, j in zip(word_boundaries[:-1], word_boundaries[1:])]
+    return [dict(word=w, tokens=t, start=float(s), end=float(e), probability=p)
+            for w, t, s, e, p in zip(words, word_tokens, start_times, end_times, probs)]
+
+
+def attach_word_timestamps(tokenizer: Tokenizer, subsegments: List[dict], alignment: List[dict],
+                           prepend_punctuations: str, append_punctuations: str,
+                           last_speech_timestamp: float) -> float:
+    """faster-whisper add_word_timestamps for one window (duration heuristics + punctuation)."""
+    text_tokens_per_sub = [[t for t in s["tokens"] if t < tokenizer.eot] for s in subsegments]
+    word_durations = np.array([w["end"] - w["start"] for w in alignment])
+    word_durations = word_durations[word_durations.nonzero()]
+    median_duration = float(np.median(word_durations)) if len(word_durations) > 0 else 0.0
+    median_duration = min(0.7, median_duration)
+    max_duration = median_duration * 2
+    if len(word_durations) > 0:
+        marks = ".。!！?？"
+        for i in range(1, len(alignment)):
+            if alignment[i]["end"] - alignment[i]["start"] > max_duration:
+                if alignment[i]["word"] in marks:
+                    alignment[i]["end"] = alignment[i]["start"] + max_duration
+                elif alignment[i - 1]["word"] in marks:
+                    alignment[i]["start"] = alignment[i]["end"] - max_duration
+    merge_punctuations(alignment, prepend_punctuations, append_punctuations)
+    word_index = 0
+    time_offset = subsegments[0]["seek"] / FRAMES_PER_SECOND if subsegments else 0.0
+    for si, sub in enumerate(subsegments):
+        saved_tokens = 0
+        words: List[dict] = []
+        while word_index < len(alignment) and saved_tokens < len(text_tokens_per_sub[si]):
+            timing = alignment[word_index]
+            if timing["word"]:
+                words.append(dict(word=timing["word"], start=round(time_offset + timing["start"], 2),
+                                  end=round(time_offset + timing["end"], 2), probability=timing["probability"]))
+            saved_tokens += len(timing["tokens"])
+            word_index += 1
+        if words:
+            # the first words after a pause must not be longer than twice the median duration
+            if words[0]["end"] - last_speech_timestamp > median_duration * 4 and (
+                    words[0]["end"] - words[0]["start"] > max_duration
+                    or (len(words) > 1 and words[1]["end"] - words[0]["start"] > max_duration * 2)):
+                if len(words) > 1 and words[1]["end"] - words[1]["start"] > max_duration:
+                    boundary = max(words[1]["end"] / 2, words[1]["end"] - max_duration)
+                    words[0]["end"] = words[1]["start"] = boundary
+                words[0]["start"] = max(0, words[0]["end"] - max_duration)
+            # prefer the segment-level timestamps when the edge words are too long
+            if sub["start"] < words[0]["end"] and sub["start"] - 0.5 > words[0]["start"]:
+                words[0]["start"] = max(0, min(words[0]["end"] - median_duration, sub["start"]))
+            else:
+                sub["start"] = words[0]["start"]
+            if sub["end"] > words[-1]["start"] and sub["end"] + 0.5 < words[-1]["end"]:
+                words[-1]["end"] = max(words[-1]["start"] + median_duration, sub["end"])
+            else:
+                sub["end"] = words[-1]["end"]
+            last_speech_timestamp = sub["end"]
+        sub["words"] = words
+    return last_speech_timestamp
+
+
+class B200WhisperModel:
+    """Drop-in for ``faster_whisper.WhisperModel`` on the surface the reference uses."""
+
+    def __init__(self, model_size_or_path: str = "base", device: str = "cuda", device_index: int = 0,
+                 compute_type: str = "bfloat16", cpu_threads: int = 0, num_workers: int = 1,
+                 download_root: Optional[str] = None, local_files_only: bool = False,
+                 state_dict=None, dims: Optional[ModelDims] = None, tokenizer_json: Optional[str] = None,
+                 alignment_heads: Optional[Sequence[Tuple[int, int]]] = None, max_batch: int = 8,
+                 max_beam: int = 5, seed: int = 0, **_ignored):
+        if device not in ("cuda", "auto"):
+            raise _lib.B200WError(f"device={device!r}: the B200 backend runs on CUDA only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise _lib.B200WError("CUDA device required: the B200 backend has no CPU fallback")
+        self.device = torch.device("cuda", device_index if isinstance(device_index, int) else device_index[0])
+        self.compute_type = "bfloat16"  # the only arithmetic this backend implements
+        self.tokenizer_json = tokenizer_json
+        name = model_size_or_path
+        if state_dict is None:
+            from .loader import load_model_dir  # real checkpoints, when a directory is given
+            loaded = load_model_dir(name)
+            if loaded is not None:
+                state_dict, dims, tj, heads = loaded
+                self.tokenizer_json = self.tokenizer_json or tj
+                alignment_heads = alignment_heads or heads
+            else:
+                base = name.replace(".en", "")
+                if base not in MODEL_DIMS:
+                    raise ValueError(f"unknown model size {name!r}")
+                dims = MODEL_DIMS[base]
+                # no checkpoints exist offline: seeded synthetic weights of the exact architecture
+                state_dict = synthetic_state_dict(dims, seed=seed)
+                if alignment_heads is None:
+                    alignment_heads = ALIGNMENT_HEADS.get(base)
+        assert dims is not None
+        self.dims = dims
+        self.alignment_heads = list(alignment_heads) if alignment_heads else default_alignment_heads(dims)
+        self.is_multilingual = dims.multilingual
+        with torch.cuda.device(self.device):
+            self.engine = WhisperEngine(dims, pack_for_engine(state_dict, dims, self.device), max_batch=max_batch,
+                                        max_beam=max_beam, device=self.device)
+        self.max_batch = max_batch
+        self.max_beam = max_beam
+        self.last_timings = {}
+
+    @property
+    def supported_languages(self) -> List[str]:
+        return Tokenizer(self.dims.n_vocab, self.is_multilingual, language="en").languages if self.is_multilingual else ["en"]
+
+    # ------------------------------------------------------------------ public API
+    def transcribe(self, audio: Union[np.ndarray, torch.Tensor], language: Optional[str] = None,
+                   task: str = "transcribe", **kw):
+        results = self.transcribe_batch([audio], languages=[language], task=task, **kw)
+        segments, info = results[0]
+        return iter(segments), info
+
+    def transcribe_batch(self, audios: Sequence[np.ndarray], languages: Optional[Sequence[Optional[str]]] = None,
+                         task: str = "transcribe", beam_size: int = 5, best_of: int = 5, patience: float = 1,
+                         length_penalty: float = 1, repetition_penalty: float = 1, no_repeat_ngram_size: int = 0,
+                         temperature: Union[float, Sequence[float]] = (0.0, 0.2, 0.4, 0.6, 0.8, 1.0),
+                         compression_ratio_threshold: Optional[float] = 2.4,
+                         log_prob_threshold: Optional[float] = -1.0, no_speech_threshold: Optional[float] = 0.6,
+                         condition_on_previous_text: bool = True, prompt_reset_on_temperature: float = 0.5,
+                         initial_prompt: Union[None, str, Sequence[Optional[str]]] = None,
+                         prefix: Optional[str] = None, suppress_blank: bool = True,
+                         suppress_tokens: Optional[List[int]] = (-1,), without_timestamps: bool = False,
+                         max_initial_timestamp: float = 1.0, word_timestamps: bool = False,
+                         prepend_punctuations: str = "\"'“¿([{-", append_punctuations: str = "\"'.。,，!！?？:：”)]}、",
+                         vad_filter: bool = False, max_new_tokens: Optional[int] = None, **unsupported):
+        """Transcribe independent clips concurrently; returns [(segments, info)] per clip."""
+        if vad_filter:
+            raise NotImplementedError("vad_filter: the VAD gate sits in the caller (Silero in the reference)")
+        if repetition_penalty != 1 or no_repeat_ngram_size != 0:
+            raise NotImplementedError("repetition_penalty / no_repeat_ngram_size are not implemented")
+        temps = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
+        if temps[0] != 0:
+            raise NotImplementedError("sampling temperatures > 0 are not implemented (temperature 0 only)")
+        if beam_size > self.max_beam:
+            raise ValueError(f"beam_size {beam_size} > engine max_beam {self.max_beam}")
+        n = len(audios)
+        languages = list(languages) if languages is not None else [None] * n
+        prompts_in = initial_prompt if isinstance(initial_prompt, (list, tuple)) else [initial_prompt] * n
+        audios = [np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1)) for a in audios]
+        options = TranscriptionOptions(beam_size, best_of, patience, length_penalty, repetition_penalty,
+                                       no_repeat_ngram_size, log_prob_threshold, no_speech_threshold,
+                                       compression_ratio_threshold, condition_on_previous_text,
+                                       prompt_reset_on_temperature, temps[:1], None, prefix, suppress_blank,
+                                       list(suppress_tokens) if suppress_tokens is not None else None,
+                                       without_timestamps, max_initial_timestamp, word_timestamps,
+                                       prepend_punctuations, append_punctuations, max_new_tokens)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        with torch.cuda.device(self.device):
+            ev[0].record()
+            audio_dev, offsets = frontend.upload_audio(audios, self.device)
+            mel = frontend.log_mel(audio_dev, offsets, self.dims.n_mels)
+            ev[1].record()
+            # language detection on the first window of the clips that need it (faster-whisper A9)
+            lang_info = [(languages[i], 1.0, None) for i in range(n)]
+            need = [i for i in range(n) if languages[i] is None]
+            if need:
+                if not self.is_multilingual:
+                    for i in need:
+                        lang_info[i] = ("en", 1.0, None)
+                else:
+                    det = self._detect_language(mel, need)
+                    for i, d in zip(need, det):
+                        lang_info[i] = d
+            streams: List[_Stream] = []
+            for i in range(n):
+                tk = Tokenizer(self.dims.n_vocab, self.is_multilingual, task=task, language=lang_info[i][0],
+                               tokenizer_json=self.tokenizer_json)
+                st = _Stream(i, mel.n_frames[i] - 1, tk, options)
+                ip = prompts_in[i]
+                if ip is not None:
+                    if isinstance(ip, str):
+                        st.all_tokens.extend(tk.encode(" " + ip.strip()))
+                    else:
+                        st.all_tokens.extend(ip)
+                streams.append(st)
+            self._run_streams(mel, streams)
+        out = []
+        for i, st in enumerate(streams):
+            info = TranscriptionInfo(lang_info[i][0], float(lang_info[i][1]), len(audios[i]) / SAMPLE_RATE,
+                                     len(audios[i]) / SAMPLE_RATE, lang_info[i][2], options)
+            out.append((st.segments, info))
+        return out
+
+    def detect_language(self, audio: np.ndarray):
+        with torch.cuda.device(self.device):
+            audio_dev, offsets = frontend.upload_audio([np.asarray(audio, dtype=np.float32)], self.device)
+            mel = frontend.log_mel(audio_dev, offsets, self.dims.n_mels)
+            lang, prob, allp = self._detect_language(mel, [0])[0]
+        return lang, prob, allp
+
+    # ------------------------------------------------------------------ internals
+    def _detect_language(self, mel: frontend.MelBatch, which: List[int]):
+        tk = Tokenizer(self.dims.n_vocab, True, language="en")
+        out = []
+        for c0 in range(0, len(which), self.max_batch):
+            ids = which[c0:c0 + self.max_batch]
+            windows = frontend.pack_windows(mel, ids, [0] * len(ids))
+            enc = self.engine.encode(windows)
+            ckv = self.engine.cross_kv(enc)
+            probs = self.engine.detect_language(ckv, tk.sot, tk.language_ids)
+            for p in probs:
+                order = np.argsort(-p, kind="stable")
+                allp = [(tk.languages[j], float(p[j])) for j in order]
+                out.append((allp[0][0], allp[0][1], allp))
+        return out
+
+    def _decode_options(self, tk: Tokenizer, o: TranscriptionOptions) -> DecodeOptions:
+        return DecodeOptions(
+            beam_size=o.beam_size, patience=o.patience, length_penalty=o.length_penalty,
+            max_new_tokens=o.max_new_tokens or 0, suppress_blank=o.suppress_blank,
+            without_timestamps=o.without_timestamps,
+            max_initial_timestamp_index=int(round(o.max_initial_timestamp / TIME_PRECISION)),
+            eot=tk.eot, sot=tk.sot, no_speech=tk.no_speech, no_timestamps=tk.no_timestamps,
+            timestamp_begin=tk.timestamp_begin,
+            suppress_ids=tk.suppressed_tokens(o.suppress_tokens) if o.suppress_tokens is not None else [],
+            blank_ids=tk.blank_tokens())
+
+    def _run_streams(self, mel: frontend.MelBatch, streams: List[_Stream]) -> None:
+        """Rounds of (pack windows -> encode -> cross K/V -> decode -> align) over the live streams."""
+        while True:
+            live = [s for s in streams if s.seek < s.content_frames]
+            if not live:
+                return
+            for c0 in range(0, len(live), self.max_batch):
+                self._round(mel, live[c0:c0 + self.max_batch])
+
+    def _round(self, mel: frontend.MelBatch, batch: List[_Stream]) -> None:
+        o = batch[0].options
+        for s in batch:
+            s.time_offset = s.seek * HOP / SAMPLE_RATE
+            s.segment_size = min(N_FRAMES, s.content_frames - s.seek)
+            s.prompt = get_prompt(s.tokenizer, s.all_tokens[s.prompt_reset_since:], o.without_timestamps, o.prefix)
+        windows = frontend.pack_windows(mel, [s.sid for s in batch], [s.seek for s in batch])
+        enc = self.engine.encode(windows)
+        ckv = self.engine.cross_kv(enc)
+        # all streams of a batch share the special-token layout; suppress lists come from stream 0
+        results = self.engine.decode(ckv, [s.prompt for s in batch], self._decode_options(batch[0].tokenizer, o))
+        to_align = []  # (stream, subsegments, text_tokens, row in ckv)
+        per_stream = []
+        for row, (s, res) in enumerate(zip(batch, results)):
+            tk = s.tokenizer
+            tokens = res.tokens
+            seq_len = len(tokens)
+            avg_logprob = res.sum_logprob / (seq_len + 1)
+            text = tk.decode(tokens).strip()
+            compression_ratio = get_compression_ratio(text) if text else 0.0
+            if o.no_speech_threshold is not None:
+                should_skip = res.no_speech_prob > o.no_speech_threshold
+                if o.log_prob_threshold is not None and avg_logprob > o.log_prob_threshold:
+                    should_skip = False
+                if should_skip:
+                    s.seek += s.segment_size
+                    per_stream.append(None)
+                    continue
+            segment_duration = s.segment_size * HOP / SAMPLE_RATE
+            subs, new_seek, single_ending = split_segments_by_timestamps(tk, tokens, s.time_offset, s.segment_size,
+                                                                        segment_duration, s.seek)
+            per_stream.append((s, subs, new_seek, single_ending, avg_logprob, compression_ratio, res.no_speech_prob))
+            if o.word_timestamps:
+                text_tokens = [t for sub in subs for t in sub["tokens"] if t < tk.eot]
+                to_align.append((len(per_stream) - 1, row, text_tokens))
+        if o.word_timestamps and to_align:
+            self._align_batch(ckv, batch, per_stream, to_align, o)
+        for entry in per_stream:
+            if entry is None:
+                continue
+            s, subs, new_seek, single_ending, avg_logprob, compression_ratio, nsp = entry
+            tk = s.tokenizer
+            if o.word_timestamps and not single_ending:
+                last_word_end = None
+                for sub in reversed(subs):
+                    if sub.get("words"):
+                        last_word_end = sub["words"][-1]["end"]
+                        break
+                if last_word_end is not None and last_word_end > s.time_offset:
+                    new_seek = round(last_word_end * FRAMES_PER_SECOND)
+            s.seek = new_seek
+            for sub in subs:
+                tokens = sub["tokens"]
+                text = tk.decode(tokens)
+                if sub["start"] == sub["end"] or not text.strip():
+                    continue
+                s.all_tokens.extend(tokens)
+                s.idx += 1
+                words = [Word(**w) for w in sub["words"]] if o.word_timestamps else None
+                s.segments.append(Segment(s.idx, sub["seek"], sub["start"], sub["end"], text, tokens, avg_logprob,
+                                          compression_ratio, nsp, words, 0.0))
+            if not o.condition_on_previous_text:
+                s.prompt_reset_since = len(s.all_tokens)
+
+    def _align_batch(self, ckv, batch, per_stream, to_align, o: TranscriptionOptions) -> None:
+        rows = [row for _, row, tt in to_align if tt]
+        if rows:
+            tk0 = batch[0].tokenizer
+            seqs, nframes = [], []
+            for _, row, tt in to_align:
+                if not tt:
+                    continue
+                tk = batch[row].tokenizer
+                seqs.append(list(tk.sot_sequence) + [tk.no_timestamps] + tt + [tk.eot])
+                nframes.append(batch[row].segment_size)
+            sub_ckv = ckv if rows == list(range(ckv.shape[0])) else ckv[rows].contiguous()
+            aligned = self.engine.align(sub_ckv, seqs, nframes, len(tk0.sot_sequence), self.alignment_heads)
+        k = 0
+        for pi, row, tt in to_align:
+            s, subs = per_stream[pi][0], per_stream[pi][1]
+            if tt:
+                ti, fi, tp = aligned[k]
+                k += 1
+                alignment = words_from_alignment(s.tokenizer, tt, ti, fi, tp)
+            else:
+                alignment = []
+            s.last_speech_timestamp = attach_word_timestamps(s.tokenizer, subs, alignment, o.prepend_punctuations,
+                                                             o.append_punctuations, s.last_speech_timestamp)
