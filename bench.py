@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-sec/sec (RTFx) of the Whisper hot path on B200.
+
+Workload (BASELINE.json configs[3], per GPU): Whisper large-v3 bf16 (128 mel bins), beam 5, 32
+concurrent synthetic 16 kHz streams per GPU (256 across 8 GPUs, weak scaling); one "step" = every
+stream submits one 30 s chunk and gets timestamped words back:
+    log-mel -> encoder -> cross K/V -> beam-5 decode (Whisper logit rules) -> word timing (DTW).
+Weights are seeded synthetic tensors of the exact large-v3 architecture (no checkpoints offline);
+the "peaked" synthetic model emits ~100-token transcripts ending in EOT, like real speech.
+
+  value     RTFx with the audio already resident in HBM when the timed region starts
+  e2e       RTFx through the public host API (numpy in, Python Segment/Word objects out):
+            pinned H2D of every chunk and D2H of the results inside the timed region
+  roofline  the dominant kernel (tcgen05 GEMM, 128x256 tiles): algorithmic flops / CUDA-event time
+            of every launch inside the timed region, vs the measured bf16 peak
+  cpu_baseline  the CPU oracle (restatement of the reference's faster-whisper path, fp32) on the
+            host cores, on a bounded sample of the same workload (rank 0, N=1 only)
+
+`--impl reference` times that CPU path as the whole run (rank 0 only under torchrun).
+One process per GPU; streams are independent, so there is no collective on the data path (NCCL is
+used only for the barrier and the max-over-ranks of the elapsed time).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 16000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="large-v3")
+    ap.add_argument("--streams", type=int, default=32, help="concurrent streams per GPU")
+    ap.add_argument("--beam", type=int, default=5)
+    ap.add_argument("--seconds", type=float, default=30.0, help="audio seconds per chunk")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-streams", type=int, default=1)
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_streams(n, seconds, rank):
+    from tests.synth import speech_like
+    return [speech_like(1234 + rank * 100000 + i, seconds) for i in range(n)]
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 200 ms (pynvml)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_mhz = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------ CPU path
+def cpu_oracle_pass(model_name, audios, beam, threads=None):
+    """One pass of the hot path on the host cores with the oracle; returns seconds elapsed.
+    (bench.py's cpu_baseline / reference arm: the only place the oracle is executed here.)"""
+    import torch
+    from oracle import align as OA
+    from oracle import decoding as OD
+    from oracle import frontend as OF
+    from oracle.model import Dims, OracleWhisper
+    from realtime_whisper_asr_b200 import weights as W
+    from realtime_whisper_asr_b200.tokenizer import Tokenizer
+
+    if threads:
+        torch.set_num_threads(threads)
+    md = W.MODEL_DIMS[model_name]
+    cache = cpu_oracle_pass.__dict__.setdefault("cache", {})
+    if model_name not in cache:
+        sd = W.synthetic_state_dict(md, seed=0)
+        dims = Dims(md.n_mels, md.d_model, md.n_heads, md.n_enc_layers, md.n_vocab, md.d_model, md.n_heads,
+                    md.n_dec_layers)
+        cache[model_name] = OracleWhisper(sd, dims, "fp32")
+    model = cache[model_name]
+    tk = Tokenizer(md.n_vocab, True, language="en")
+    opts = OD.DecodeOptions(beam_size=beam, eot=tk.eot, sot=tk.sot, no_speech=tk.no_speech,
+                            no_timestamps=tk.no_timestamps, timestamp_begin=tk.timestamp_begin,
+                            suppress_ids=tk.suppressed_tokens([-1]), blank_ids=tk.blank_tokens())
+    heads = W.ALIGNMENT_HEADS.get(model_name) or W.default_alignment_heads(md)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for a in audios:
+            mel = OF.log_mel(a, md.n_mels)
+            nfr = mel.shape[-1] - 1
+            win = OF.pad_or_trim(mel[:, :3000])
+            enc = model.encode(torch.from_numpy(win[None]))
+            res = OD.decode_one(model, enc[0], tk.sot_sequence, opts)
+            text = [t for t in res.tokens if t < tk.eot]
+            if text:
+                OA.align(model, enc[0], tk.sot_sequence, tk.no_timestamps, tk.eot, text, min(nfr, 3000), heads)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    audios = make_streams(args.cpu_sample_streams, args.seconds, 0)
+    for _ in range(min(args.warmup, 1)):  # one warm-up pass builds the weights and pages them in
+        cpu_oracle_pass(args.model, audios, args.beam)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_oracle_pass(args.model, audios, args.beam)
+    audio_s = args.steps * len(audios) * args.seconds
+    value = audio_s / t
+    sample = (f"{len(audios)} of {args.streams} streams per step, one {args.seconds:g} s chunk each, "
+              f"full path (log-mel, encoder, beam-{args.beam} decode, word timing), fp32 PyTorch on the host")
+    line = {
+        "impl": "reference", "metric": "audio-sec/sec per GPU (RTFx)", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle port (faster-whisper/CTranslate2 are not installable offline); reported, not a target",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"whisper {args.model} bf16, beam {args.beam}, {args.streams} concurrent 16 kHz streams "
+                        f"per GPU x {args.seconds:g} s chunk per step, word timestamps on "
+                        "(BASELINE.json configs[3] per-GPU share)",
+            "streams_per_gpu": args.streams, "chunk_seconds": args.seconds, "beam_size": args.beam,
+            "weights": "seeded synthetic (peaked transcript circuit), exact architecture",
+            "cache_note": "inputs larger than L2 (3.1 GB of weights + 61 MB of audio per step)",
+            "parallelism": "independent streams sharded over GPUs, no collective"}
+
+
+# ------------------------------------------------------------------------------------ GPU path
+def run_b200(args, rank, world, local):
+    import torch
+    from realtime_whisper_asr_b200 import _lib
+    from realtime_whisper_asr_b200 import frontend as FE
+    from realtime_whisper_asr_b200.transcribe import B200WhisperModel
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    model = B200WhisperModel(args.model, device="cuda", device_index=local, max_batch=args.streams,
+                             max_beam=max(args.beam, 1))
+    audios = make_streams(args.streams, args.seconds, rank)
+    kw = dict(languages=["en"] * args.streams, beam_size=args.beam, temperature=0.0, word_timestamps=True,
+              condition_on_previous_text=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg: audio uploaded once, outside the timed region
+    audio_dev, offsets = FE.upload_audio(audios, dev)
+    torch.cuda.synchronize()
+    n_words = 0
+    for _ in range(args.warmup):
+        out = model.transcribe_batch(None, device_audio=(audio_dev, offsets), **kw)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    import ctypes as C
+    _lib.check(lib.b200w_gemm_profile_begin(256))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = model.transcribe_batch(None, device_audio=(audio_dev, offsets), **kw)
+    ev1.record()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = _lib.launch_count() - launches0
+    tms, tfl, tn = C.c_double(), C.c_double(), C.c_int64()
+    _lib.check(lib.b200w_gemm_profile_end(C.byref(tms), C.byref(tfl), C.byref(tn)))
+    n_words = sum(len(s.words) for segs, _ in out for s in segs)
+    n_tokens = sum(len(s.tokens) for segs, _ in out for s in segs)
+
+    # ---- end-to-end leg: host numpy in, Python objects out, every step
+    for _ in range(max(1, args.warmup // 3)):
+        model.transcribe_batch(audios, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        out2 = model.transcribe_batch(audios, **kw)
+    ev1.record()
+    barrier()
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    audio_s = world * args.streams * args.seconds * args.steps
+    value = audio_s / (dev_ms / 1000.0)
+    e2e = audio_s / (e2e_ms / 1000.0)
+    h2d = int(sum(len(a) for a in audios) * 4)
+    # D2H per step: sampled tokens + log-probs + no-speech (decode), DTW paths + token probs (align)
+    d2h = int(args.streams * (448 * 4 + 8 + (448 + 1502) * 8 + 448 * 4))
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    achieved = (tfl.value / 1e12) / (tms.value / 1e3) if tms.value > 0 else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256,4>", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+                "peak_source": peak_src, "launches_timed": int(tn.value),
+                "kernel_ms_per_step": tms.value / args.steps, "share_of_step": tms.value / dev_ms if dev_ms else None}
+
+    if rank != 0:
+        return
+    line = {
+        "metric": "audio-sec/sec per GPU (RTFx)", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args),
+        "per_gpu_value": value / world,
+        "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "tokens_per_step": n_tokens, "words_per_step": n_words,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample_audios = audios[: args.cpu_sample_streams]
+        t = cpu_oracle_pass(args.model, sample_audios, args.beam, threads=cores)
+        line["cpu_baseline"] = {
+            "value": len(sample_audios) * args.seconds / t, "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "sample": f"{len(sample_audios)} of {args.streams} streams, one {args.seconds:g} s chunk, full path, "
+                      f"fp32 PyTorch oracle on the host ({t:.1f} s of CPU work)"}
+    print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

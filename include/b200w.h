@@ -35,6 +35,12 @@ int b200w_abi_version(void);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 uint64_t b200w_launch_count(void);
 
+/* Measurement hook: record CUDA events around every GEMM launch of one tile-width class
+ * (bn = 64 | 128 | 256) until _end, which synchronises those events and returns the summed device
+ * time (ms), the summed algorithmic flops (2*M*N*K per launch) and the launch count. */
+int b200w_gemm_profile_begin(int bn);
+int b200w_gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches);
+
 /* ---------------------------------------------------------------- front end (HBM-bound) ------ */
 
 /* Log-mel features of n_streams clips (faster-whisper FeatureExtractor.__call__, padding=160).

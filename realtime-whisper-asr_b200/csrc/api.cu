@@ -35,6 +35,19 @@ const char* b200w_last_error(void) { return get_last_error(); }
 int b200w_abi_version(void) { return B200W_ABI_VERSION; }
 uint64_t b200w_launch_count(void) { return g_launch_count; }
 
+int b200w_gemm_profile_begin(int bn) {
+  B200W_API_BEGIN
+  gemm_profile_begin(bn);
+  B200W_API_END
+}
+int b200w_gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches) {
+  B200W_API_BEGIN
+  long long n = 0;
+  gemm_profile_end(total_ms, total_flops, &n);
+  *launches = n;
+  B200W_API_END
+}
+
 int b200w_logmel(const float* audio_dev, const int64_t* offsets_dev, const int64_t* out_offsets_dev,
                  const int32_t* tile_prefix_dev, int n_streams, int total_tiles, int n_mels,
                  float* out_dev, int32_t* stream_max_dev, int max_frames, void* stream) {

@@ -8,6 +8,7 @@
 #include "gemm.h"
 
 #include <mutex>
+#include <vector>
 
 #include "ptx.cuh"
 
@@ -268,6 +269,46 @@ void make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t
   }
 }
 
+// ---- optional per-launch timing (bench.py's roofline leg): CUDA events around every launch of
+// one tile-width class, recorded on the launching stream; read back after a synchronize.
+struct ProfSlot {
+  cudaEvent_t beg, end;
+  double flops;
+};
+static int g_prof_bn = 0;  // 0 = off, else the BN class being timed
+static std::vector<ProfSlot> g_prof_slots;
+static size_t g_prof_used = 0;
+
+void gemm_profile_begin(int bn) {
+  g_prof_bn = bn;
+  g_prof_used = 0;
+}
+void gemm_profile_end(double* total_ms, double* total_flops, long long* launches) {
+  g_prof_bn = 0;
+  double ms = 0, fl = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    float t = 0.f;
+    B200W_CHECK_CUDA(cudaEventSynchronize(g_prof_slots[i].end));
+    B200W_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof_slots[i].beg, g_prof_slots[i].end));
+    ms += t;
+    fl += g_prof_slots[i].flops;
+  }
+  *total_ms = ms;
+  *total_flops = fl;
+  *launches = (long long)g_prof_used;
+}
+static ProfSlot* prof_slot(double flops) {
+  if (g_prof_used == g_prof_slots.size()) {
+    ProfSlot s;
+    B200W_CHECK_CUDA(cudaEventCreate(&s.beg));
+    B200W_CHECK_CUDA(cudaEventCreate(&s.end));
+    g_prof_slots.push_back(s);
+  }
+  ProfSlot* s = &g_prof_slots[g_prof_used++];
+  s->flops = flops;
+  return s;
+}
+
 template <int BN, int STAGES>
 static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p,
                         cudaStream_t stream) {
@@ -281,7 +322,14 @@ static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmPara
   p.n_tiles = cdiv(p.N, BN);
   p.total_tiles = p.n_tiles * p.m_tiles_per_batch * p.batches;
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  ProfSlot* ps = nullptr;
+  if (g_prof_bn == BN) {
+    // algorithmic flops: 2 * M * N * K with M = produced rows
+    ps = prof_slot(2.0 * (double)p.out_rows * p.batches * (double)p.N * (double)p.total_kb * BK);
+    B200W_CHECK_CUDA(cudaEventRecord(ps->beg, stream));
+  }
   gemm_tcgen05_kernel<BN, STAGES><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p);
+  if (ps) B200W_CHECK_CUDA(cudaEventRecord(ps->end, stream));
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }

@@ -335,8 +335,12 @@ class B200WhisperModel:
                          suppress_tokens: Optional[List[int]] = (-1,), without_timestamps: bool = False,
                          max_initial_timestamp: float = 1.0, word_timestamps: bool = False,
                          prepend_punctuations: str = "\"'“¿([{-", append_punctuations: str = "\"'.。,，!！?？:：”)]}、",
-                         vad_filter: bool = False, max_new_tokens: Optional[int] = None, **unsupported):
-        """Transcribe independent clips concurrently; returns [(segments, info)] per clip."""
+                         vad_filter: bool = False, max_new_tokens: Optional[int] = None,
+                         device_audio=None, **unsupported):
+        """Transcribe independent clips concurrently; returns [(segments, info)] per clip.
+
+        ``device_audio=(audio_dev, offsets)`` skips the host->device copy: the clips are already
+        concatenated in one fp32 device tensor (``audios`` is then only used for its length)."""
         if vad_filter:
             raise NotImplementedError("vad_filter: the VAD gate sits in the caller (Silero in the reference)")
         if repetition_penalty != 1 or no_repeat_ngram_size != 0:
@@ -346,10 +350,14 @@ class B200WhisperModel:
             raise NotImplementedError("sampling temperatures > 0 are not implemented (temperature 0 only)")
         if beam_size > self.max_beam:
             raise ValueError(f"beam_size {beam_size} > engine max_beam {self.max_beam}")
-        n = len(audios)
+        n = len(audios) if device_audio is None else len(device_audio[1]) - 1
         languages = list(languages) if languages is not None else [None] * n
         prompts_in = initial_prompt if isinstance(initial_prompt, (list, tuple)) else [initial_prompt] * n
-        audios = [np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1)) for a in audios]
+        if device_audio is None:
+            audios = [np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1)) for a in audios]
+            durations = [len(a) / SAMPLE_RATE for a in audios]
+        else:
+            durations = [float(x) / SAMPLE_RATE for x in np.diff(device_audio[1])]
         options = TranscriptionOptions(beam_size, best_of, patience, length_penalty, repetition_penalty,
                                        no_repeat_ngram_size, log_prob_threshold, no_speech_threshold,
                                        compression_ratio_threshold, condition_on_previous_text,
@@ -360,7 +368,10 @@ class B200WhisperModel:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         with torch.cuda.device(self.device):
             ev[0].record()
-            audio_dev, offsets = frontend.upload_audio(audios, self.device)
+            if device_audio is None:
+                audio_dev, offsets = frontend.upload_audio(audios, self.device)
+            else:
+                audio_dev, offsets = device_audio
             mel = frontend.log_mel(audio_dev, offsets, self.dims.n_mels)
             ev[1].record()
             # language detection on the first window of the clips that need it (faster-whisper A9)
@@ -389,8 +400,8 @@ class B200WhisperModel:
             self._run_streams(mel, streams)
         out = []
         for i, st in enumerate(streams):
-            info = TranscriptionInfo(lang_info[i][0], float(lang_info[i][1]), len(audios[i]) / SAMPLE_RATE,
-                                     len(audios[i]) / SAMPLE_RATE, lang_info[i][2], options)
+            info = TranscriptionInfo(lang_info[i][0], float(lang_info[i][1]), durations[i], durations[i],
+                                     lang_info[i][2], options)
             out.append((st.segments, info))
         return out
 
