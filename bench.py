@@ -247,6 +247,14 @@ def run_b200(args, rank, world, local):
     launches = _lib.launch_count() - launches0
     tms, tfl, tn = C.c_double(), C.c_double(), C.c_int64()
     _lib.check(lib.b200w_gemm_profile_end(C.byref(tms), C.byref(tfl), C.byref(tn)))
+    # one extra, untimed pass with per-phase synchronisation: where the step goes (stderr only)
+    model.profile_phases = True
+    model.last_timings = {}
+    model.transcribe_batch(None, device_audio=(audio_dev, offsets), **kw)
+    model.profile_phases = False
+    if rank == 0:
+        print("phase seconds (1 step, synchronised): " +
+              ", ".join(f"{k}={v:.3f}" for k, v in model.last_timings.items() if k != "_"), file=sys.stderr)
     n_words = sum(len(s.words) for segs, _ in out for s in segs)
     n_tokens = sum(len(s.tokens) for segs, _ in out for s in segs)
 

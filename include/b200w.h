@@ -122,7 +122,7 @@ int b200w_engine_finalize(b200w_engine* e);
 int b200w_encode(b200w_engine* e, const void* windows_dev, int B, void* enc_out_dev, void* stream);
 
 /* Cross-attention K/V of every decoder layer, once per chunk (one GEMM over all layers):
- * enc_out bf16 [B][1500][d] -> cross_kv bf16 [B][1500][n_dec_layers][2][d]. */
+ *  enc_out bf16 [B][1500][d] -> cross_kv bf16 [B][n_dec_layers][2][heads][1500][64] (head-major). */
 int b200w_cross_kv(b200w_engine* e, const void* enc_out_dev, int B, void* cross_kv_dev, void* stream);
 
 typedef struct b200w_decode_opts {

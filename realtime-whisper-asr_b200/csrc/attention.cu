@@ -322,4 +322,157 @@ void dec_attention(const DecAttnParams& p, int n_heads, cudaStream_t stream) {
   B200W_CHECK_CUDA(cudaGetLastError());
 }
 
+
+// ------------------------------------------------------------------- cross attention (decode)
+// Every hypothesis of a stream attends to the same per-chunk cross K/V, so one CTA serves up to
+// XQ consecutive query rows of one stream for one head and reads that head's K and V exactly once:
+// 16 warps split the 1500 keys, scores for all queries live in shared memory, one warp per query
+// normalises, and the P.V product is accumulated per warp and reduced through shared memory.
+static constexpr int XQ = 8;    // queries per CTA
+static constexpr int XW = 16;   // warps per CTA
+
+__global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnParams p) {
+  extern __shared__ float xs[];
+  const int len = p.len;
+  const int len_pad = (len + 31) & ~31;
+  float* s_q = xs;                          // [XQ][64]
+  float* s_inv = s_q + XQ * HD;             // [XQ]
+  float* s_sc = s_inv + XQ;                 // [XQ][len_pad]
+  float* s_acc = s_sc + XQ * len_pad;       // [XW][XQ][64]
+  const int g = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = p.g_start[g], nq = p.g_count[g];
+  const long long base = p.kv_base_off[p.stream[q0]];
+  const bf16* kb = p.kbase + base + h * p.head_stride;
+  const bf16* vb = p.vbase + base + h * p.head_stride;
+
+  for (int i = tid; i < XQ * HD; i += XW * 32) {
+    const int q = i >> 6, c = i & 63;
+    s_q[i] = q < nq ? __bfloat162float(p.q[(long long)(q0 + q) * p.q_stride + h * HD + c]) * p.scale : 0.f;
+  }
+  __syncthreads();
+
+  // scores: one key per lane per pass
+  for (int key = tid; key < len_pad; key += XW * 32) {
+    float acc[XQ];
+#pragma unroll
+    for (int q = 0; q < XQ; ++q) acc[q] = 0.f;
+    if (key < len) {
+      const bf16* kp = kb + (long long)key * p.kv_row_stride;
+#pragma unroll
+      for (int c = 0; c < HD; c += 8) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(kp + c));
+        const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+        float kf[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __bfloat1622float2(u2[t]);
+          kf[2 * t] = f.x;
+          kf[2 * t + 1] = f.y;
+        }
+#pragma unroll
+        for (int q = 0; q < XQ; ++q) {
+          const float4 qa = *reinterpret_cast<const float4*>(s_q + q * HD + c);
+          const float4 qb = *reinterpret_cast<const float4*>(s_q + q * HD + c + 4);
+          acc[q] = fmaf(qa.x, kf[0], acc[q]); acc[q] = fmaf(qa.y, kf[1], acc[q]);
+          acc[q] = fmaf(qa.z, kf[2], acc[q]); acc[q] = fmaf(qa.w, kf[3], acc[q]);
+          acc[q] = fmaf(qb.x, kf[4], acc[q]); acc[q] = fmaf(qb.y, kf[5], acc[q]);
+          acc[q] = fmaf(qb.z, kf[6], acc[q]); acc[q] = fmaf(qb.w, kf[7], acc[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < XQ; ++q) s_sc[q * len_pad + key] = key < len ? acc[q] : -INFINITY;
+  }
+  __syncthreads();
+
+  // softmax: warp q owns query q
+  if (warp < nq) {
+    float* sc = s_sc + warp * len_pad;
+    float mx = -INFINITY;
+    for (int i = lane; i < len; i += 32) mx = fmaxf(mx, sc[i]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int i = lane; i < len_pad; i += 32) {
+      const float e = i < len ? __expf(sc[i] - mx) : 0.f;
+      sc[i] = e;
+      sum += e;
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    if (lane == 0) s_inv[warp] = inv;
+    const int ex = p.head_export ? p.head_export[h] : -1;
+    if (ex >= 0) {
+      float* dst = p.probs_out + ((long long)ex * p.n_queries + q0 + warp) * p.probs_stride;
+      for (int i = lane; i < len; i += 32) dst[i] = sc[i] * inv;
+    }
+  }
+  __syncthreads();
+
+  // P.V: half-warps take alternate keys, 16 lanes x 4 dims cover the head
+  {
+    const int half = lane >> 4, l16 = lane & 15;
+    float acc[XQ][4];
+#pragma unroll
+    for (int q = 0; q < XQ; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+    const bf16* vl = vb + 4 * l16;
+    for (int k0 = warp * 2 + half; k0 < len_pad; k0 += 4 * XW * 2) {
+      uint2 v[4];
+      int kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        kk[u] = k0 + u * XW * 2;
+        v[u] = kk[u] < len ? __ldg(reinterpret_cast<const uint2*>(vl + (long long)kk[u] * p.kv_row_stride))
+                           : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (kk[u] >= len_pad) continue;
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[u].x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[u].y));
+#pragma unroll
+        for (int q = 0; q < XQ; ++q) {
+          const float pw = s_sc[q * len_pad + kk[u]];
+          acc[q][0] = fmaf(pw, a.x, acc[q][0]); acc[q][1] = fmaf(pw, a.y, acc[q][1]);
+          acc[q][2] = fmaf(pw, b.x, acc[q][2]); acc[q][3] = fmaf(pw, b.y, acc[q][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < XQ; ++q)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[q][c] += __shfl_xor_sync(0xffffffffu, acc[q][c], 16);
+    if (half == 0) {
+#pragma unroll
+      for (int q = 0; q < XQ; ++q)
+        *reinterpret_cast<float4*>(s_acc + ((warp * XQ + q) * HD) + 4 * l16) =
+            make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+    }
+  }
+  __syncthreads();
+  {
+    const int q = tid >> 6, c = tid & 63;  // 512 threads = XQ x 64 outputs
+    if (q < nq) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < XW; ++w) sum += s_acc[(w * XQ + q) * HD + c];
+      p.out[(long long)(q0 + q) * p.out_stride + h * HD + c] = __float2bfloat16(sum * s_inv[q]);
+    }
+  }
+}
+
+void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, cudaStream_t stream) {
+  if (n_groups <= 0) return;
+  const int len_pad = (p.len + 31) & ~31;
+  const size_t smem = sizeof(float) * (XQ * HD + XQ + (size_t)XQ * len_pad + (size_t)XW * XQ * HD);
+  static size_t configured = 0;
+  if (smem > configured) {
+    B200W_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  cross_attn_kernel<<<dim3(n_groups, n_heads), XW * 32, smem, stream>>>(p);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
 }  // namespace b200w

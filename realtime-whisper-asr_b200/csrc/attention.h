@@ -31,4 +31,30 @@ struct DecAttnParams {
 };
 void dec_attention(const DecAttnParams& p, int n_heads, cudaStream_t stream);
 
+// Cross attention for the decoder: groups of up to 8 consecutive query rows of the SAME stream
+// (beams of one chunk, or consecutive prompt / teacher-forced tokens) share one pass over that
+// stream's K/V.  K/V of position t, head h: kbase/vbase + kv_base_off[stream] + h * head_stride + t * kv_row_stride.
+struct CrossAttnParams {
+  const bf16* q = nullptr;
+  int q_stride = 0;
+  const bf16* kbase = nullptr;
+  const bf16* vbase = nullptr;
+  long long kv_row_stride = 0;             // elements between consecutive positions
+  long long head_stride = 64;              // elements between consecutive heads
+  const long long* kv_base_off = nullptr;  // [streams]
+  const int* stream = nullptr;             // [n_queries] stream of each query row
+  const int* g_start = nullptr;            // [n_groups] first query row of the group
+  const int* g_count = nullptr;            // [n_groups] rows in the group (1..8)
+  int len = 0;                             // keys per stream (1500)
+  bf16* out = nullptr;
+  int out_stride = 0;
+  float scale = 0.125f;
+  int n_queries = 0;
+  float* probs_out = nullptr;              // optional [n_export][n_queries][probs_stride]
+  const int* head_export = nullptr;        // [n_heads] -> export index or -1
+  int probs_stride = 0;
+};
+void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, cudaStream_t stream);
+static constexpr int CROSS_GROUP = 8;
+
 }  // namespace b200w

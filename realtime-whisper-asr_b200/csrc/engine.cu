@@ -10,6 +10,7 @@
 #include "../../include/b200w.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -25,6 +26,8 @@
 using namespace b200w;
 
 namespace {
+
+constexpr int HEAD_DIM = 64;
 
 struct Weight {
   const void* ptr;
@@ -72,8 +75,10 @@ struct DevBuf {
 struct PinnedBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  bool grew = false;  // set when the address changed (captured graphs must be dropped)
   void alloc(size_t n) {
     if (n > bytes) {
+      grew = p != nullptr;
       if (p) cudaFreeHost(p);
       p = nullptr;
       B200W_CHECK_CUDA(cudaMallocHost(&p, n));
@@ -121,8 +126,23 @@ struct b200w_engine {
   DevBuf meta;                                        // per-pass int metadata
   DevBuf cross_off, const_len, mask, topk_ids, topk_lp, probs, head_export;
   DevBuf al_w, al_mat, al_trace, al_path, al_plen, scratch_i;
+  DevBuf d_split;        // fp32 split-K partial sums of the GEMM feeding the residual stream
+  SplitReduce pending;   // partial sums of the last decoder GEMM, folded in by the next LayerNorm
   PinnedBuf h_meta, h_out;
   long long total_slots = 0;
+
+  // decode-step CUDA graphs, keyed by everything that is baked into the captured launches
+  struct StepGraph {
+    const void* ckv;
+    int B, K, parity;
+    int opts_hash;
+    cudaGraphExec_t exec;
+  };
+  std::vector<StepGraph> step_graphs;
+  bool use_graphs = true;
+  unsigned long long launches_per_step = 0;
+  cudaStream_t own_stream = nullptr;  // decode runs here (the legacy default stream cannot be captured)
+  cudaEvent_t join_event = nullptr;
 };
 
 namespace {
@@ -175,10 +195,46 @@ void linear(const bf16* A, int M, int K, const Lin& l, int N, void* out, int64_t
   gemm_bf16(g, s);
 }
 
+// x += A W^T + b for the decoder's residual stream.  Skinny calls (decode steps) are split along K so
+// that enough CTAs stream the weights; the partial sums are handed to the next LayerNorm.
+SplitReduce residual_linear(b200w_engine* e, const bf16* A, int M, int K, const Lin& l, float* x, cudaStream_t s) {
+  const int d = e->d;
+  const int splits = gemm_suggest_splits(M, d, K);
+  if (splits <= 1 || (size_t)splits * M * d * 4 > e->d_split.bytes) {
+    linear(A, M, K, l, d, x, d, 1, 0, x, 1, d, s);
+    return SplitReduce{};
+  }
+  GemmDesc g;
+  g.A = A;
+  g.a_rows = M;
+  g.a_cols = K;
+  g.a_row_stride = K;
+  g.W = l.w;
+  g.N = d;
+  g.K = K;
+  g.w_row_stride = K;
+  g.out_rows = M;
+  g.out = e->d_split.p;
+  g.out_fp32 = 1;
+  g.out_row_stride = d;
+  g.split_k = splits;
+  g.split_stride = (int64_t)M * d;
+  g.force_bn = 64;
+  gemm_bf16(g, s);
+  SplitReduce r;
+  r.partial = e->d_split.as<float>();
+  r.n = splits;
+  r.stride = (long long)M * d;
+  r.bias = l.b;
+  return r;
+}
+
 // ----------------------------------------------------------------------------------- decoder pass
 struct PassMeta {  // device pointers into e->meta for one forward pass of n tokens
   int n = 0;
   int *tok, *pos, *slot, *trow, *kvlen, *stream, *parent;
+  int *g_start, *g_count;  // cross-attention groups: runs of <= 8 rows of one stream
+  int n_groups = 0;
   int4* state;
 };
 
@@ -197,10 +253,23 @@ struct HostMeta {
   }
 };
 
-PassMeta upload_meta(b200w_engine* e, const HostMeta& h, cudaStream_t s) {
+// Stage the metadata of one pass in the pinned buffer and return the device-side view.  The layout
+// depends only on (n, number of groups), so a decode step of fixed shape always produces the same
+// pointers -- which is what lets the step be replayed as a CUDA graph.
+PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) {
   const int n = h.n();
   B200W_REQUIRE(n <= e->n_max, "too many decoder tokens in one pass");
-  const size_t ints = (size_t)n * 7, bytes = ints * 4 + (size_t)n * 16 + 16;
+  // cross-attention groups: consecutive rows of the same stream, at most CROSS_GROUP per group
+  std::vector<int> gs, gc;
+  for (int i = 0; i < n;) {
+    int j = i + 1;
+    while (j < n && j - i < CROSS_GROUP && h.stream[j] == h.stream[i]) ++j;
+    gs.push_back(i);
+    gc.push_back(j - i);
+    i = j;
+  }
+  const int ng = (int)gs.size();
+  const size_t ints = (size_t)n * 7 + 2 * (size_t)ng, bytes = ints * 4 + (size_t)n * 16 + 16;
   e->h_meta.alloc(bytes);
   int* hp = e->h_meta.as<int>();
   memcpy(hp, h.tok.data(), n * 4);
@@ -210,16 +279,28 @@ PassMeta upload_meta(b200w_engine* e, const HostMeta& h, cudaStream_t s) {
   memcpy(hp + 4 * n, h.kvlen.data(), n * 4);
   memcpy(hp + 5 * n, h.stream.data(), n * 4);
   memcpy(hp + 6 * n, h.parent.data(), n * 4);
+  memcpy(hp + 7 * n, gs.data(), ng * 4);
+  memcpy(hp + 7 * n + ng, gc.data(), ng * 4);
   const size_t st_off = (ints * 4 + 15) / 16 * 16;
   memcpy(reinterpret_cast<char*>(hp) + st_off, h.state.data(), (size_t)n * 16);
-  B200W_CHECK_CUDA(cudaMemcpyAsync(e->meta.p, hp, st_off + (size_t)n * 16, cudaMemcpyHostToDevice, s));
+  *copy_bytes = st_off + (size_t)n * 16;
   PassMeta m;
   m.n = n;
   int* dp = e->meta.as<int>();
   m.tok = dp; m.pos = dp + n; m.slot = dp + 2 * n; m.trow = dp + 3 * n; m.kvlen = dp + 4 * n;
   m.stream = dp + 5 * n;
   m.parent = dp + 6 * n;
+  m.g_start = dp + 7 * n;
+  m.g_count = dp + 7 * n + ng;
+  m.n_groups = ng;
   m.state = reinterpret_cast<int4*>(reinterpret_cast<char*>(dp) + st_off);
+  return m;
+}
+
+PassMeta upload_meta(b200w_engine* e, const HostMeta& h, cudaStream_t s) {
+  size_t bytes = 0;
+  PassMeta m = fill_host_meta(e, h, &bytes);
+  B200W_CHECK_CUDA(cudaMemcpyAsync(e->meta.p, e->h_meta.p, bytes, cudaMemcpyHostToDevice, s));
   return m;
 }
 
@@ -240,12 +321,13 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
   bf16* cq = e->d_cq.as<bf16>();
   bf16* mlp = e->d_mlp.as<bf16>();
   embed_tokens(m.tok, m.pos, e->tok_emb, e->dec_pos, x, n, d, s);
+  SplitReduce pend;
   for (int l = 0; l < e->Ld; ++l) {
     const DecLayer& L = e->dec[l];
     bf16* kp = e->kpool.as<bf16>() + (long long)l * e->total_slots * d;
     bf16* vp = e->vpool.as<bf16>() + (long long)l * e->total_slots * d;
     // self attention
-    layernorm(x, nullptr, L.ln1.g, L.ln1.b, h, n, d, s);
+    layernorm(x, nullptr, L.ln1.g, L.ln1.b, h, n, d, s, &pend);
     linear(h, n, d, L.qkv, 3 * d, qkv, 3 * d, 0, 0, nullptr, 0, 0, s);
     kv_scatter(qkv, m.slot, kp, vp, n, d, s);
     DecAttnParams a;
@@ -254,37 +336,43 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     a.table = table; a.table_stride = e->Tctx; a.trow = m.trow; a.kvlen = m.kvlen;
     a.out = attn; a.out_stride = d; a.scale = 0.125f; a.n_queries = n; a.max_len = max_kvlen;
     dec_attention(a, e->H, s);
-    linear(attn, n, d, L.out, d, x, d, 1, 0, x, 1, d, s);
+    pend = residual_linear(e, attn, n, d, L.out, x, s);
     // cross attention
-    layernorm(x, nullptr, L.ln2.g, L.ln2.b, h, n, d, s);
+    layernorm(x, nullptr, L.ln2.g, L.ln2.b, h, n, d, s, &pend);
     linear(h, n, d, L.cq, d, cq, d, 0, 0, nullptr, 0, 0, s);
-    DecAttnParams c;
+    CrossAttnParams c;
     c.q = cq; c.q_stride = d;
-    c.kbase = cross_kv + (long long)l * 2 * d;
-    c.vbase = cross_kv + (long long)l * 2 * d + d;
-    c.kv_row_stride = (long long)e->Ld * 2 * d;
-    c.table = nullptr; c.trow = m.stream; c.kv_base_off = e->cross_off.as<long long>();
-    c.kvlen = e->const_len.as<int>();
-    c.out = attn; c.out_stride = d; c.scale = 0.125f; c.n_queries = n; c.max_len = e->Tenc;
+    // cross K/V layout [stream][layer][k|v][head][1500][64]
+    c.kbase = cross_kv + (long long)(2 * l) * e->Tenc * d;
+    c.vbase = cross_kv + (long long)(2 * l + 1) * e->Tenc * d;
+    c.kv_row_stride = HEAD_DIM;
+    c.head_stride = (long long)e->Tenc * HEAD_DIM;
+    c.kv_base_off = e->cross_off.as<long long>();
+    c.stream = m.stream;
+    c.g_start = m.g_start; c.g_count = m.g_count;
+    c.len = e->Tenc;
+    c.out = attn; c.out_stride = d; c.scale = 0.125f; c.n_queries = n;
     if (ax && ax->layer_has[l]) {
       c.head_export = ax->head_table + (long long)l * e->H;
       c.probs_out = ax->probs;
       c.probs_stride = e->Tenc;
     }
-    dec_attention(c, e->H, s);
-    linear(attn, n, d, L.cout, d, x, d, 1, 0, x, 1, d, s);
+    cross_attention(c, m.n_groups, e->H, s);
+    pend = residual_linear(e, attn, n, d, L.cout, x, s);
     // MLP
-    layernorm(x, nullptr, L.ln3.g, L.ln3.b, h, n, d, s);
+    layernorm(x, nullptr, L.ln3.g, L.ln3.b, h, n, d, s, &pend);
     linear(h, n, d, L.fc1, 4 * d, mlp, 4 * d, 0, 1, nullptr, 0, 0, s);
-    linear(mlp, n, 4 * d, L.fc2, d, x, d, 1, 0, x, 1, d, s);
+    pend = residual_linear(e, mlp, n, 4 * d, L.fc2, x, s);
   }
+  e->pending = pend;  // folded in by the final LayerNorm (logits_for_rows)
 }
 
 // final LayerNorm on selected rows + tied-embedding logits -> e->logits[0 .. n_sel)
 void logits_for_rows(b200w_engine* e, const int* sel_rows_dev, int n_sel, cudaStream_t s) {
   B200W_REQUIRE(n_sel <= e->logit_rows, "logits buffer too small");
   bf16* hsel = e->d_hsel.as<bf16>();
-  layernorm(e->d_x.as<float>(), sel_rows_dev, e->dec_ln.g, e->dec_ln.b, hsel, n_sel, e->d, s);
+  layernorm(e->d_x.as<float>(), sel_rows_dev, e->dec_ln.g, e->dec_ln.b, hsel, n_sel, e->d, s, &e->pending);
+  if (!sel_rows_dev) e->pending = SplitReduce{};  // written back into x: must not be added twice
   Lin emb;
   emb.w = e->tok_emb;
   emb.b = nullptr;
@@ -326,10 +414,13 @@ int b200w_engine_destroy(b200w_engine* e) {
                       &e->d_attn, &e->d_cq, &e->d_mlp, &e->d_hsel, &e->kpool, &e->vpool, &e->tables[0],
                       &e->tables[1], &e->logits, &e->meta, &e->cross_off, &e->const_len, &e->mask,
                       &e->topk_ids, &e->topk_lp, &e->probs, &e->head_export, &e->al_w, &e->al_mat,
-                      &e->al_trace, &e->al_path, &e->al_plen, &e->scratch_i};
+                      &e->al_trace, &e->al_path, &e->al_plen, &e->scratch_i, &e->d_split};
     for (DevBuf* b : bufs) b->release();
     e->h_meta.release();
     e->h_out.release();
+    for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.exec);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->join_event) cudaEventDestroy(e->join_event);
     delete e;
   }
   B200W_API_END
@@ -395,6 +486,7 @@ int b200w_engine_finalize(b200w_engine* e) {
   e->d_attn.alloc(n * d * 2);
   e->d_cq.alloc(n * d * 2);
   e->d_mlp.alloc(n * 4 * d * 2);
+  e->d_split.alloc((size_t)(128 * 160 * 64) * 16 * 4);  // splits only happen below ~148 tiles
   e->slots_per_stream = e->Tctx * e->cfg.max_beam;
   e->total_slots = (long long)e->slots_per_stream * Bm;
   e->kpool.alloc((size_t)e->Ld * e->total_slots * d * 2);
@@ -405,7 +497,7 @@ int b200w_engine_finalize(b200w_engine* e) {
   e->logit_rows = (int)std::max<int64_t>(2 * rows, 1024);
   e->logits.alloc((size_t)e->logit_rows * e->ldv * 4);
   e->d_hsel.alloc((size_t)e->logit_rows * d * 2);
-  e->meta.alloc((size_t)n * 7 * 4 + (size_t)n * 16 + 64);
+  e->meta.alloc((size_t)n * 9 * 4 + (size_t)n * 16 + 64);
   e->scratch_i.alloc(((size_t)e->logit_rows + 4 * Bm + n) * 4);
   e->cross_off.alloc(Bm * 8);
   e->const_len.alloc(n * 4);
@@ -421,6 +513,13 @@ int b200w_engine_finalize(b200w_engine* e) {
     std::vector<int> cl(n, (int)T);
     B200W_CHECK_CUDA(cudaMemcpy(e->const_len.p, cl.data(), n * 4, cudaMemcpyHostToDevice));
   }
+  // pinned staging buffers get their final size here: captured decode graphs hold their addresses
+  e->h_meta.alloc((size_t)n * 9 * 4 + (size_t)n * 16 + 64);
+  e->h_out.alloc(std::max<size_t>({(size_t)rows * MAX_TOPK * 8 + 64, (size_t)Bm * (e->Tctx + T + 4) * 8 + Bm * 8,
+                                   (size_t)Bm * 128 * 4}));
+  B200W_CHECK_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  B200W_CHECK_CUDA(cudaEventCreateWithFlags(&e->join_event, cudaEventDisableTiming));
+  e->use_graphs = getenv("B200W_NO_GRAPHS") == nullptr;
   e->finalized = true;
   B200W_API_END
 }
@@ -458,8 +557,22 @@ int b200w_cross_kv(b200w_engine* e, const void* enc_out_dev, int B, void* cross_
   B200W_REQUIRE(e && e->finalized, "engine not finalized");
   B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
   const int N = e->Ld * 2 * e->d;
-  linear(static_cast<const bf16*>(enc_out_dev), B * e->Tenc, e->d, e->cross_kv, N, cross_kv_dev, N, 0, 0,
-         nullptr, 0, 0, static_cast<cudaStream_t>(stream));
+  GemmDesc g;
+  g.A = static_cast<const bf16*>(enc_out_dev);
+  g.a_rows = B * e->Tenc;
+  g.a_cols = e->d;
+  g.a_row_stride = e->d;
+  g.W = e->cross_kv.w;
+  g.N = N;
+  g.K = e->d;
+  g.w_row_stride = e->d;
+  g.out_rows = B * e->Tenc;
+  g.bias = e->cross_kv.b;
+  g.out = cross_kv_dev;
+  g.out_row_stride = N;
+  g.head_major_T = e->Tenc;  // -> [B][L][2][H][1500][64]: each head's keys are one contiguous block
+  g.head_major_d = e->d;
+  gemm_bf16(g, static_cast<cudaStream_t>(stream));
   B200W_API_END
 }
 
@@ -515,7 +628,10 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
   B200W_REQUIRE(e && e->finalized, "engine not finalized");
   B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
   B200W_REQUIRE(opts && opts->beam_size >= 1 && opts->beam_size <= e->cfg.max_beam, "beam size out of range");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // everything below runs on the engine's own stream, ordered after the caller's stream
+  cudaStream_t s = e->own_stream;
+  B200W_CHECK_CUDA(cudaEventRecord(e->join_event, static_cast<cudaStream_t>(stream)));
+  B200W_CHECK_CUDA(cudaStreamWaitEvent(s, e->join_event, 0));
   const b200w_decode_opts& o = *opts;
   const int K = o.beam_size, k_top = K == 1 ? 1 : 2 * K;
   const bf16* ckv = static_cast<const bf16*>(cross_kv_dev);
@@ -635,50 +751,93 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     if (!S.done && S.max_new <= 1) finish_stream(S);
   }
 
-  // ---- autoregressive steps
+  // ---- autoregressive steps.  Fixed shape: row r = b*K + k for every (stream, beam slot), whether
+  // it is live or not (idle rows decode a dummy token into a scratch slot), so that every step
+  // issues the same launches on the same buffers and can be replayed as a CUDA graph.
+  const int n_rows = B * K;
+  const int opts_hash = o.eot * 31 + o.timestamp_begin * 17 + o.max_initial_timestamp_index * 7 + k_top +
+                        (o.without_timestamps ? 1000003 : 0);
+  B200W_CHECK_CUDA(cudaMemsetAsync(e->tables[cur ^ 1].p, 0, (size_t)e->cfg.max_batch * e->cfg.max_beam * Tctx * 4, s));
+  auto enqueue_step = [&](const PassMeta& m, size_t meta_bytes, int from) {
+    B200W_CHECK_CUDA(cudaMemcpyAsync(e->meta.p, e->h_meta.p, meta_bytes, cudaMemcpyHostToDevice, s));
+    // fork the page tables: new[row] = old[parent][0:pos] + [slot]
+    gather_fork_tables(e->tables[from].as<int>(), m.parent, m.trow, m.pos, m.slot, e->tables[from ^ 1].as<int>(),
+                       m.n, Tctx, s);
+    decoder_forward(e, ckv, m, e->tables[from ^ 1].as<int>(), Tctx, nullptr, s);
+    logits_for_rows(e, nullptr, m.n, s);
+    SampleParams sps = sp;
+    sps.state = m.state;
+    sample_topk(sps, m.n, s);
+    B200W_CHECK_CUDA(cudaMemcpyAsync(h_ids, sp.out_ids, (size_t)m.n * k_top * 4, cudaMemcpyDeviceToHost, s));
+    B200W_CHECK_CUDA(cudaMemcpyAsync(h_lp, sp.out_logprobs, (size_t)m.n * k_top * 4, cudaMemcpyDeviceToHost, s));
+  };
   for (int step = 1;; ++step) {
     hm.clear();
-    struct RowRef { int b, k; };
-    std::vector<RowRef> rows;
-    int max_kv = 0;
+    bool any = false;
     for (int b = 0; b < B; ++b) {
       StreamState& S = st[b];
-      if (S.done) continue;
-      for (int k = 0; k < (int)S.alive.size(); ++k) {
-        Hyp& h = S.alive[k];
-        const int pos = S.P + step - 1;
-        const int slot = b * e->slots_per_stream + S.P + (step - 1) * K + k;
-        const int new_row = b * K + k;
-        hm.push(h.tokens.back(), pos, slot, new_row, pos + 1, b, sampling_state(h.tokens, o), h.table_row);
-        h.table_row = new_row;
-        rows.push_back({b, k});
-        max_kv = std::max(max_kv, pos + 1);
+      for (int k = 0; k < K; ++k) {
+        const int row = b * K + k;
+        if (!S.done && k < (int)S.alive.size()) {
+          Hyp& h = S.alive[k];
+          const int pos = S.P + step - 1;
+          const int slot = b * e->slots_per_stream + S.P + (step - 1) * K + k;
+          hm.push(h.tokens.back(), pos, slot, row, pos + 1, b, sampling_state(h.tokens, o), h.table_row);
+          h.table_row = row;
+          any = true;
+        } else {  // idle row: one dummy token at position 0 in a scratch slot of its own
+          hm.push(o.eot, 0, b * e->slots_per_stream + e->slots_per_stream - 1 - k, row, 1, b,
+                  make_int4(0, 0, 0, 0), row);
+        }
       }
     }
-    const int n = hm.n();
-    if (n == 0) break;
-    pm = upload_meta(e, hm, s);
-    // fork the page tables: new[row] = old[parent][0:pos] + [slot]
-    {
-      const int nxt = cur ^ 1;
-      gather_fork_tables(e->tables[cur].as<int>(), pm.parent, pm.trow, pm.pos, pm.slot,
-                         e->tables[nxt].as<int>(), n, Tctx, s);
-      cur = nxt;
+    if (!any) break;
+    size_t meta_bytes = 0;
+    pm = fill_host_meta(e, hm, &meta_bytes);
+    cudaGraphExec_t exec = nullptr;
+    if (e->h_meta.grew || e->h_out.grew) {  // staging buffers moved: captured addresses are stale
+      for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.exec);
+      e->step_graphs.clear();
+      e->h_meta.grew = e->h_out.grew = false;
     }
-    decoder_forward(e, ckv, pm, e->tables[cur].as<int>(), max_kv, nullptr, s);
-    logits_for_rows(e, nullptr, n, s);
-    sp.state = pm.state;
-    sample_topk(sp, n, s);
-    B200W_CHECK_CUDA(cudaMemcpyAsync(h_ids, sp.out_ids, (size_t)n * k_top * 4, cudaMemcpyDeviceToHost, s));
-    B200W_CHECK_CUDA(cudaMemcpyAsync(h_lp, sp.out_logprobs, (size_t)n * k_top * 4, cudaMemcpyDeviceToHost, s));
+    if (e->use_graphs && step >= 2) {
+      for (auto& g : e->step_graphs)
+        if (g.ckv == ckv && g.B == B && g.K == K && g.parity == cur && g.opts_hash == opts_hash) exec = g.exec;
+      if (!exec) {
+        cudaGraph_t graph = nullptr;
+        B200W_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        try {
+          enqueue_step(pm, meta_bytes, cur);
+        } catch (...) {
+          cudaStreamEndCapture(s, &graph);
+          if (graph) cudaGraphDestroy(graph);
+          throw;
+        }
+        B200W_CHECK_CUDA(cudaStreamEndCapture(s, &graph));
+        B200W_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        B200W_CHECK_CUDA(cudaGraphDestroy(graph));
+        if (e->step_graphs.size() >= 16) {
+          for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.exec);
+          e->step_graphs.clear();
+        }
+        e->step_graphs.push_back({ckv, B, K, cur, opts_hash, exec});
+      }
+      B200W_CHECK_CUDA(cudaGraphLaunch(exec, s));
+      g_launch_count += e->launches_per_step;
+    } else {
+      const unsigned long long before = g_launch_count;
+      enqueue_step(pm, meta_bytes, cur);
+      e->launches_per_step = g_launch_count - before;
+    }
+    cur ^= 1;
     B200W_CHECK_CUDA(cudaStreamSynchronize(s));
 
     // host-side beam bookkeeping
-    int r0 = 0;
     for (int b = 0; b < B; ++b) {
       StreamState& S = st[b];
       if (S.done) continue;
       const int na = (int)S.alive.size();
+      const int r0 = b * K;
       struct Cand { double score; int k, tok; float lp; };
       std::vector<Cand> cands;
       cands.reserve((size_t)na * k_top);
@@ -689,7 +848,6 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
           if (tok == 0x7fffffff || !(lp > -INFINITY)) continue;
           cands.push_back({S.alive[k].cum + (double)lp, k, tok, lp});
         }
-      r0 += na;
       std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& c) {
         if (a.score != c.score) return a.score > c.score;
         if (a.k != c.k) return a.k < c.k;

@@ -31,17 +31,29 @@ struct GemmParams {
   void* out;
   int out_fp32;
   long long out_rs, out_bs;
+  int hm_T, hm_d;  // head-major scatter of the output (cross K/V layout) when hm_T > 0
+  int splits;      // split-K: > 1 => split s writes its partial sums (fp32) to out + s * split_stride
+  long long split_stride;
 };
 
 // 32 accumulator columns of one output row -> global memory.
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int b,
-                                               int r, int n) {
-  const long long out_off = (long long)b * p.out_bs + (long long)r * p.out_rs;
+                                               int r, int n, int ks) {
+  long long out_off = (long long)b * p.out_bs + (long long)r * p.out_rs + (long long)ks * p.split_stride;
   const long long res_off = (long long)b * p.res_bs + (long long)r * p.res_rs;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int ng = n + 8 * g;
     if (ng >= p.N) break;
+    if (p.hm_T > 0) {
+      // row = (stream, t), column = (slab = layer*2 + k|v, head, c): store at
+      // [stream][slab][head][t][64] so that one head's keys are a contiguous [T][64] block
+      const int stream = r / p.hm_T, t = r - stream * p.hm_T;
+      const int slab = ng / p.hm_d, within = ng - slab * p.hm_d;
+      const int head = within >> 6, c = within & 63;
+      const int n_slabs = p.N / p.hm_d, n_heads = p.hm_d >> 6;
+      out_off = ((((long long)stream * n_slabs + slab) * n_heads + head) * p.hm_T + t) * 64 + c - ng;
+    }
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[8 * g + j]);
@@ -150,14 +162,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
       uint32_t stage = 0, phase = 0;
+      const int mn_tiles = p.total_tiles / p.splits;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+        const int nt = mn % p.n_tiles, mt = mn / p.n_tiles;
         const int b = mt / p.m_tiles_per_batch;
         const int r0 = (mt % p.m_tiles_per_batch) * BM;
         const int n0 = nt * BN;
+        // split-K (single tap only): this CTA owns k-blocks [kb_lo, kb_hi)
+        const int kb_lo = (int)((long long)p.total_kb * ks / p.splits);
+        const int kb_hi = (int)((long long)p.total_kb * (ks + 1) / p.splits);
         int kbg = 0;
         for (int t = 0; t < p.n_taps; ++t) {
           for (int kb = 0; kb < p.tap_kb[t]; ++kb, ++kbg) {
+            if (kbg < kb_lo || kbg >= kb_hi) continue;
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t fb = full0 + 8 * stage;
             mbar_arrive_expect_tx(fb, A_BYTES + B_BYTES);
@@ -173,11 +191,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {  // ---------------- MMA issuer
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const int mn_tiles = p.total_tiles / p.splits;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int ks = tile / mn_tiles;
+        const int n_kb = (int)((long long)p.total_kb * (ks + 1) / p.splits) - (int)((long long)p.total_kb * ks / p.splits);
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.total_kb; ++kb) {
+        for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
           const uint64_t ad = make_sw128_desc(smem_u32(sA + stage * A_BYTES));
@@ -195,8 +216,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {  // ---------------- epilogue warps 2..5 (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
     uint32_t acc = 0, acc_phase = 0;
+    const int mn_tiles = p.total_tiles / p.splits;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+      const int nt = mn % p.n_tiles, mt = mn / p.n_tiles;
       const int b = mt / p.m_tiles_per_batch;
       const int r = (mt % p.m_tiles_per_batch) * BM + q * 32 + lane;
       const int n0 = nt * BN;
@@ -213,7 +236,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_before();
           mbar_arrive(tempty0 + 8 * acc);
         }
-        if (row_ok && n0 + c0 < p.N) epilogue_chunk(p, v, b, r, n0 + c0);
+        if (row_ok && n0 + c0 < p.N) epilogue_chunk(p, v, b, r, n0 + c0, ks);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -321,6 +344,7 @@ static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmPara
   }
   p.n_tiles = cdiv(p.N, BN);
   p.total_tiles = p.n_tiles * p.m_tiles_per_batch * p.batches;
+  p.total_tiles *= p.splits;
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   ProfSlot* ps = nullptr;
   if (g_prof_bn == BN) {
@@ -377,7 +401,16 @@ void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   p.out_fp32 = d.out_fp32;
   p.out_rs = d.out_row_stride;
   p.out_bs = d.out_batch_stride;
-
+  p.hm_T = d.head_major_T;
+  p.hm_d = d.head_major_d;
+  // split-K: every split stores its fp32 partial sums in its own slab of `out`
+  // ([splits][rows][out_row_stride]); the consumer (LayerNorm) adds the slabs in a fixed order, so
+  // results do not depend on scheduling.  Bias / activation / residual are the consumer's job.
+  p.splits = d.split_k > 1 ? d.split_k : 1;
+  p.split_stride = d.split_stride;
+  B200W_REQUIRE(p.splits == 1 || (d.out_fp32 && !d.bias && !d.residual && d.act == 0 && d.n_taps == 0 &&
+                                  d.batches == 1 && d.head_major_T == 0 && d.split_stride > 0),
+                "split-K needs a plain fp32 partial-sum output");
   // Tile width: widest tile that still gives every SM work; narrow tiles for skinny (decode) GEMMs.
   int bn = d.force_bn;
   if (bn == 0) {
@@ -395,6 +428,17 @@ void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   else if (bn == 128) launch_gemm<128, 6>(tmA, tmB, p, stream);
   else if (bn == 64) launch_gemm<64, 8>(tmA, tmB, p, stream);
   else throw Error("force_bn must be 64, 128 or 256");
+}
+
+int gemm_suggest_splits(int M, int N, int K) {
+  // skinny GEMMs (decode steps): enough CTAs to stream the weights at full HBM bandwidth
+  // the split count depends on (N, K) only, so a row's result does not change with the number of
+  // rows batched next to it (as long as the call stays below the one-wave threshold)
+  if (cdiv(M, BM) * cdiv(N, 64) >= num_sms()) return 1;
+  const int want = cdiv(num_sms(), cdiv(N, 64));
+  const int kb = K / BK;
+  int sp = want < kb / 4 ? want : kb / 4;
+  return sp < 1 ? 1 : (sp > 16 ? 16 : sp);
 }
 
 void conv1d_k3(const bf16* x, const bf16* w, const float* bias, const float* addend, void* out, int B,

@@ -33,9 +33,19 @@ struct GemmDesc {
   int out_fp32 = 0;
   int64_t out_row_stride = 0, out_batch_stride = 0;  // elements; row stride % 8 == 0
   int force_bn = 0;  // 0 = heuristic; else 64 / 128 / 256
+  // Head-major scatter of the output (used for the decoder's cross K/V): rows are (stream, t) with
+  // head_major_T positions per stream, columns are (slab, head, 64); element goes to
+  // out[stream][slab][head][t][64].  0 = plain row-major output.
+  int head_major_T = 0, head_major_d = 0;
+  // split-K (n > 1): split s stores its fp32 partial sums at out + s * split_stride (plain
+  // stores, no bias / activation / residual); the consumer adds the slabs in order (deterministic).
+  int split_k = 1;
+  int64_t split_stride = 0;
 };
 
 void gemm_bf16(const GemmDesc& d, cudaStream_t stream);
+// number of K splits that gives a skinny [M x N x K] GEMM enough CTAs (1 = do not split)
+int gemm_suggest_splits(int M, int N, int K);
 
 // conv1d, kernel 3, padding 1, stride 1|2 over time-major x bf16 [B][T][C]; w bf16 [N][3C] tap-major;
 // out = GELU(conv + bias) + addend (fp32 [T_out][N], shared by all batches; may be null).

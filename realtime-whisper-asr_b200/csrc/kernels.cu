@@ -8,17 +8,20 @@
 namespace b200w {
 
 // ------------------------------------------------------------------------------- LayerNorm
-// one warp per row; x fp32 (optionally gathered through row_idx) -> y bf16.  d % 128 == 0, d <= 1280
-__global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict__ x,
-                                                        const int* __restrict__ row_idx,
+// one warp per row; x fp32 (optionally gathered through row_idx) -> y bf16.  d % 128 == 0, d <= 1280.
+// Optional fused split-K reduce: x[row] += bias + sum_s partial[s][row] (slabs added in order) before
+// the normalisation; the sum is written back to x unless rows are gathered.
+__global__ void __launch_bounds__(128) layernorm_kernel(float* __restrict__ x, const int* __restrict__ row_idx,
                                                         const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta,
-                                                        bf16* __restrict__ y, int rows, int d) {
+                                                        const float* __restrict__ beta, bf16* __restrict__ y,
+                                                        int rows, int d, const float* __restrict__ partial,
+                                                        int n_partial, long long partial_stride,
+                                                        const float* __restrict__ pbias) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const long long src = row_idx ? row_idx[row] : row;
-  const float4* xp = reinterpret_cast<const float4*>(x + src * d);
+  float4* xp = reinterpret_cast<float4*>(x + src * d);
   const int nv = d >> 7;  // float4 per lane
   float4 v[10];
   float sum = 0.f;
@@ -26,6 +29,15 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
   for (int i = 0; i < 10; ++i)
     if (i < nv) {
       v[i] = xp[lane + 32 * i];
+      if (n_partial > 0) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(pbias) + lane + 32 * i);
+        v[i].x += bb.x; v[i].y += bb.y; v[i].z += bb.z; v[i].w += bb.w;
+        for (int s = 0; s < n_partial; ++s) {
+          const float4 pp = reinterpret_cast<const float4*>(partial + s * partial_stride + src * d)[lane + 32 * i];
+          v[i].x += pp.x; v[i].y += pp.y; v[i].z += pp.z; v[i].w += pp.w;
+        }
+        if (!row_idx) xp[lane + 32 * i] = v[i];
+      }
       sum += v[i].x + v[i].y + v[i].z + v[i].w;
     }
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -57,11 +69,14 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
     }
 }
 
-void layernorm(const float* x, const int* row_idx, const float* gamma, const float* beta, bf16* y,
-               int rows, int d, cudaStream_t stream) {
+void layernorm(float* x, const int* row_idx, const float* gamma, const float* beta, bf16* y, int rows, int d,
+               cudaStream_t stream, const SplitReduce* sr) {
   if (rows <= 0) return;
   B200W_REQUIRE(d % 128 == 0 && d <= 1280, "LayerNorm width must be a multiple of 128, <= 1280");
-  layernorm_kernel<<<cdiv(rows, 4), 128, 0, stream>>>(x, row_idx, gamma, beta, y, rows, d);
+  const bool red = sr && sr->n > 0;
+  layernorm_kernel<<<cdiv(rows, 4), 128, 0, stream>>>(x, row_idx, gamma, beta, y, rows, d,
+                                                       red ? sr->partial : nullptr, red ? sr->n : 0,
+                                                       red ? sr->stride : 0, red ? sr->bias : nullptr);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }

@@ -4,8 +4,16 @@
 
 namespace b200w {
 
-void layernorm(const float* x, const int* row_idx, const float* gamma, const float* beta, bf16* y,
-               int rows, int d, cudaStream_t stream);
+// Pending split-K partial sums of the GEMM that feeds the residual stream: [n][rows][d] fp32 slabs
+// `stride` elements apart, plus that GEMM's bias.  LayerNorm folds them into x (in slab order).
+struct SplitReduce {
+  const float* partial = nullptr;
+  int n = 0;
+  long long stride = 0;
+  const float* bias = nullptr;
+};
+void layernorm(float* x, const int* row_idx, const float* gamma, const float* beta, bf16* y, int rows, int d,
+               cudaStream_t stream, const SplitReduce* sr = nullptr);
 void embed_tokens(const int* tok, const int* pos, const bf16* tok_emb, const float* pos_emb, float* x,
                   int n, int d, cudaStream_t stream);
 void kv_scatter(const bf16* qkv, const int* slot, bf16* kpool, bf16* vpool, int n, int d,

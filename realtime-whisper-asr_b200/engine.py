@@ -103,10 +103,10 @@ class WhisperEngine:
         return out
 
     def cross_kv(self, enc_out: torch.Tensor) -> torch.Tensor:
-        """bf16 [B, 1500, d] -> bf16 [B, 1500, L_dec, 2, d]."""
+        """bf16 [B, 1500, d] -> bf16 [B, L_dec, 2, heads, 1500, 64] (head-major: one head's keys contiguous)."""
         B = enc_out.shape[0]
         assert B <= self.max_batch
-        out = torch.empty((B, self.dims.n_audio_ctx, self.dims.n_dec_layers, 2, self.dims.d_model),
+        out = torch.empty((B, self.dims.n_dec_layers, 2, self.dims.n_heads, self.dims.n_audio_ctx, 64),
                           dtype=torch.bfloat16, device=self.device)
         _lib.check(self.lib.b200w_cross_kv(self._h, enc_out.data_ptr(), B, out.data_ptr(), self._stream()))
         return out

@@ -1,0 +1,158 @@
+"""Host scheduler for many concurrent streams.
+
+The reference is single-stream (one OnlineASRProcessor on the main thread,
+/root/reference/一键实时识别麦克风.py:1450-1513) and picks one GPU by free memory (:208-213).  At
+scale the unit of parallelism is the stream: every ``transcribe`` call depends only on that
+stream's buffer and prompt, so
+  * across GPUs streams are SHARDED (sticky, by rank) with no data-path collective: one process
+    per GPU, replicated weights; ``torch.distributed`` is used only for barriers and for the
+    max-over-ranks of timings (NCCL on GPUs, gloo in the CPU tests);
+  * inside a GPU concurrent calls are BATCHED: ``StreamBatcher`` gathers the calls that arrive
+    within a short window and runs them as one ``transcribe_batch`` (one encoder / decoder / align
+    launch sequence for all of them), each caller getting exactly what a solo call would return.
+``BatchedASR`` is a ``B200WhisperASR`` whose ``transcribe`` goes through the batcher, so several
+stream processors (one thread each, as the reference's loop would be per stream) share one engine.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from dataclasses import dataclass, field
+from typing import Any, Dict, Hashable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .backend import B200WhisperASR
+
+
+def shard_streams(stream_ids: Sequence[Hashable], world_size: int) -> Dict[int, List[Hashable]]:
+    """Sticky partition of streams over ranks: sorted ids dealt round-robin, so that a stream keeps
+    its GPU (prompt / KV locality) as long as the set of streams does not change."""
+    ids = sorted(stream_ids, key=lambda x: (str(type(x)), x))
+    return {r: ids[r::world_size] for r in range(world_size)}
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Timing reduction used by every multi-GPU number: the slowest rank defines the step."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+@dataclass
+class _Request:
+    audio: np.ndarray
+    language: Optional[str]
+    initial_prompt: Optional[str]
+    key: Tuple
+    kwargs: Dict[str, Any]
+    done: threading.Event = field(default_factory=threading.Event)
+    result: Any = None
+    error: Optional[BaseException] = None
+
+
+class StreamBatcher:
+    """Dynamic batching of concurrent ``model.transcribe`` calls onto one engine."""
+
+    def __init__(self, model, max_batch: Optional[int] = None, max_wait_ms: float = 2.0):
+        self.model = model
+        self.max_batch = max_batch or getattr(model, "max_batch", 8)
+        self.max_wait = max_wait_ms / 1000.0
+        self._lock = threading.Condition()
+        self._pending: List[_Request] = []
+        self._stop = False
+        self.batches_run = 0
+        self.requests_run = 0
+        self._thread = threading.Thread(target=self._loop, name="b200w-batcher", daemon=True)
+        self._thread.start()
+
+    def transcribe(self, audio, language=None, initial_prompt=None, **kwargs):
+        """Same contract as ``B200WhisperModel.transcribe``; blocks until this call's batch ran."""
+        key = tuple(sorted((k, repr(v)) for k, v in kwargs.items()))
+        req = _Request(np.asarray(audio, dtype=np.float32), language, initial_prompt, key, kwargs)
+        with self._lock:
+            if self._stop:
+                raise RuntimeError("StreamBatcher is closed")
+            self._pending.append(req)
+            self._lock.notify_all()
+        req.done.wait()
+        if req.error is not None:
+            raise req.error
+        segments, info = req.result
+        return iter(segments), info
+
+    def close(self):
+        with self._lock:
+            self._stop = True
+            self._lock.notify_all()
+        self._thread.join(timeout=5)
+
+    def _take_batch(self) -> List[_Request]:
+        with self._lock:
+            while not self._pending and not self._stop:
+                self._lock.wait()
+            if self._stop and not self._pending:
+                return []
+            deadline = time.monotonic() + self.max_wait
+            while len(self._pending) < self.max_batch:
+                left = deadline - time.monotonic()
+                if left <= 0:
+                    break
+                self._lock.wait(timeout=left)
+            key = self._pending[0].key
+            batch = [r for r in self._pending if r.key == key][: self.max_batch]
+            taken = set(id(r) for r in batch)
+            self._pending = [r for r in self._pending if id(r) not in taken]
+            return batch
+
+    def _loop(self):
+        while True:
+            batch = self._take_batch()
+            if not batch:
+                return
+            try:
+                out = self.model.transcribe_batch([r.audio for r in batch], languages=[r.language for r in batch],
+                                                  initial_prompt=[r.initial_prompt for r in batch], **batch[0].kwargs)
+                for r, o in zip(batch, out):
+                    r.result = o
+            except BaseException as e:  # delivered to every caller of the batch, as a solo call would raise
+                for r in batch:
+                    r.error = e
+            self.batches_run += 1
+            self.requests_run += len(batch)
+            for r in batch:
+                r.done.set()
+
+
+class _BatchedModel:
+    """``model``-shaped view that routes ``transcribe`` through a StreamBatcher."""
+
+    def __init__(self, batcher: StreamBatcher):
+        self._batcher = batcher
+
+    def transcribe(self, audio, language=None, initial_prompt=None, **kw):
+        return self._batcher.transcribe(audio, language=language, initial_prompt=initial_prompt, **kw)
+
+    def __getattr__(self, name):
+        return getattr(self._batcher.model, name)
+
+
+class BatchedASR(B200WhisperASR):
+    """One per stream; all instances that share ``batcher`` are served by one engine in batches."""
+
+    def __init__(self, lan, batcher: StreamBatcher, **kw):
+        super().__init__(lan, model=_BatchedModel(batcher), **kw)

@@ -311,6 +311,7 @@ class B200WhisperModel:
         self.max_batch = max_batch
         self.max_beam = max_beam
         self.last_timings = {}
+        self.profile_phases = False
 
     @property
     def supported_languages(self) -> List[str]:
@@ -448,17 +449,32 @@ class B200WhisperModel:
             for c0 in range(0, len(live), self.max_batch):
                 self._round(mel, live[c0:c0 + self.max_batch])
 
+    def _phase(self, name: str, t0: float) -> float:
+        """Accumulate wall time per phase when profiling is on (synchronises the device)."""
+        if not self.profile_phases:
+            return t0
+        import time as _t
+        torch.cuda.synchronize(self.device)
+        now = _t.perf_counter()
+        self.last_timings[name] = self.last_timings.get(name, 0.0) + (now - t0)
+        return now
+
     def _round(self, mel: frontend.MelBatch, batch: List[_Stream]) -> None:
+        import time as _t
         o = batch[0].options
+        t = self._phase("_", _t.perf_counter())
         for s in batch:
             s.time_offset = s.seek * HOP / SAMPLE_RATE
             s.segment_size = min(N_FRAMES, s.content_frames - s.seek)
             s.prompt = get_prompt(s.tokenizer, s.all_tokens[s.prompt_reset_since:], o.without_timestamps, o.prefix)
         windows = frontend.pack_windows(mel, [s.sid for s in batch], [s.seek for s in batch])
         enc = self.engine.encode(windows)
+        t = self._phase("encode", t)
         ckv = self.engine.cross_kv(enc)
+        t = self._phase("cross_kv", t)
         # all streams of a batch share the special-token layout; suppress lists come from stream 0
         results = self.engine.decode(ckv, [s.prompt for s in batch], self._decode_options(batch[0].tokenizer, o))
+        t = self._phase("decode", t)
         to_align = []  # (stream, subsegments, text_tokens, row in ckv)
         per_stream = []
         for row, (s, res) in enumerate(zip(batch, results)):
@@ -485,6 +501,7 @@ class B200WhisperModel:
                 to_align.append((len(per_stream) - 1, row, text_tokens))
         if o.word_timestamps and to_align:
             self._align_batch(ckv, batch, per_stream, to_align, o)
+        t = self._phase("align", t)
         for entry in per_stream:
             if entry is None:
                 continue
