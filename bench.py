@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--beam", type=int, default=5)
     ap.add_argument("--seconds", type=float, default=30.0, help="audio seconds per chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip the front-end roofline and base-latency legs")
     ap.add_argument("--cpu-sample-streams", type=int, default=1)
     return ap.parse_args()
 
@@ -192,6 +193,69 @@ def workload_config(args):
             "parallelism": "independent streams sharded over GPUs, no collective"}
 
 
+# ------------------------------------------------------------------------------------ side legs
+def frontend_leg(dev, peaks):
+    """BASELINE.json configs[4]: 1 h of synthetic audio as 120 x 30 s rows -> log-mel (80 and 128
+    bins) + dedup features of 3600 x 1 s chunks; HBM roofline with the algorithmic bytes of
+    SURVEY.md section 8d (4 B/sample in + 4 B x n_mels per 160 samples out)."""
+    import torch
+    from realtime_whisper_asr_b200 import frontend as FE
+    n_rows, n = 120, 480000
+    g = torch.Generator(device=dev).manual_seed(5)
+    audio_dev = (torch.rand(n_rows * n, generator=g, device=dev) - 0.5) * 0.2
+    offsets = np.arange(n_rows + 1, dtype=np.int64) * n
+    chunk_offsets = np.arange(3600 + 1, dtype=np.int64) * 16000
+    out = {}
+    hbm = (peaks.get("hbm_gbs") or 6650.0)
+    for name, fn, alg_bytes in (
+            ("logmel80", lambda: FE.log_mel(audio_dev, offsets, 80), n_rows * n * 4 + n_rows * 3001 * 80 * 4),
+            ("logmel128", lambda: FE.log_mel(audio_dev, offsets, 128), n_rows * n * 4 + n_rows * 3001 * 128 * 4),
+            ("dedup_1s_chunks", lambda: FE.dedup_features(audio_dev, chunk_offsets), n_rows * n * 4 + 3600 * 20)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1000.0 / reps
+        gbs = alg_bytes / (us * 1e-6) / 1e9
+        out[name] = {"us_per_hour_of_audio": us, "algorithmic_bytes": alg_bytes, "achieved_GBs": gbs,
+                     "frac_of_hbm_peak": gbs / hbm, "audio_s_per_s": 3600.0 / (us * 1e-6)}
+    out["note"] = ("input 230 MB > L2; 3 launches per log-mel call (init, mel, finalize); the finalize pass "
+                   "re-reads the features (counted once in algorithmic bytes)")
+    return out
+
+
+def latency_leg(local):
+    """BASELINE.json configs[1]: Whisper base, one live-style stream, 1 s increments (buffer trimmed
+    at 15 s as the reference's OnlineASRProcessor does), beam 5: latency of one transcribe() call."""
+    import torch
+    from realtime_whisper_asr_b200.backend import B200WhisperASR
+    from realtime_whisper_asr_b200.transcribe import B200WhisperModel
+    from tests.synth import speech_like
+    model = B200WhisperModel("base", device="cuda", device_index=local, max_batch=1, max_beam=5)
+    asr = B200WhisperASR("en", model=model, transcribe_kwargs={"beam_size": 5, "temperature": 0.0})
+    audio = speech_like(4321, 30.0)
+    lat = []
+    for i in range(1, 31):
+        buf = audio[max(0, i - 15) * 16000: i * 16000]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = asr.transcribe(buf, init_prompt="previous words")
+        asr.ts_words(res)
+        lat.append((time.perf_counter() - t0) * 1000.0)
+    lat = np.array(lat[3:])
+    del asr, model
+    torch.cuda.empty_cache()
+    return {"model": "base", "beam_size": 5, "calls": int(len(lat)), "p50_ms": float(np.percentile(lat, 50)),
+            "p90_ms": float(np.percentile(lat, 90)),
+            "what": "wall time of one backend transcribe()+ts_words() call on a 1..15 s buffer, host numpy in"}
+
+
 # ------------------------------------------------------------------------------------ GPU path
 def run_b200(args, rank, world, local):
     import torch
@@ -314,6 +378,14 @@ def run_b200(args, rank, world, local):
         "roofline": roofline,
         "tokens_per_step": n_tokens, "words_per_step": n_words,
     }
+    if world == 1 and not args.no_side_legs:
+        del model
+        torch.cuda.empty_cache()
+        try:
+            line["frontend"] = frontend_leg(dev, peaks)
+            line["latency"] = latency_leg(local)
+        except Exception as ex:  # side legs must never cost the headline number
+            line["side_leg_error"] = repr(ex)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sample_audios = audios[: args.cpu_sample_streams]

@@ -81,19 +81,20 @@ class OracleWhisper:
             w = torch.softmax((q @ k.transpose(-1, -2)) * 0.125, dim=-1)
             o = w @ v
         else:
-            # same schedule as the CUDA kernel: 128-key blocks, running max, probabilities rounded
-            # to bf16 (relative to the running max of that moment) before the P.V product
+            # same schedule as the CUDA kernel: 64-key blocks, running max, probabilities rounded
+            # to bf16 (relative to the running max of that moment) before the P.V product, row
+            # sums taken before the rounding
             c = 0.125 * 1.4426950408889634
             m = torch.full((B, n_head, T, 1), -float("inf"))
             l = torch.zeros((B, n_head, T, 1))
             o = torch.zeros((B, n_head, T, 64))
-            for j0 in range(0, T, 128):
-                s = q @ k[:, :, j0:j0 + 128].transpose(-1, -2)
+            for j0 in range(0, T, 64):
+                s = q @ k[:, :, j0:j0 + 64].transpose(-1, -2)
                 m_new = torch.maximum(m, s.max(dim=-1, keepdim=True).values * c)
                 alpha = torch.exp2(m - m_new)
-                p = _bf(torch.exp2(s * c - m_new))
+                p = torch.exp2(s * c - m_new)
                 l = l * alpha + p.sum(dim=-1, keepdim=True)
-                o = o * alpha + p @ v[:, :, j0:j0 + 128]
+                o = o * alpha + _bf(p) @ v[:, :, j0:j0 + 64]
                 m = m_new
             o = o / l
         return o.transpose(1, 2).reshape(B, T, d)

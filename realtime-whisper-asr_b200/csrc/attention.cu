@@ -16,9 +16,8 @@
 namespace b200w {
 
 static constexpr int QT = 128;   // queries per CTA
-static constexpr int KT = 128;   // keys per inner block
 static constexpr int HD = 64;    // head dim
-static constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB
+static constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: a [128][64] bf16 tile
 
 struct EncAttnParams {
   int T, d;
@@ -26,16 +25,23 @@ struct EncAttnParams {
   bf16* out;  // [B][T][d]
 };
 
-__global__ void __launch_bounds__(128, 2)
-enc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const EncAttnParams p) {
+// KT = keys per inner block (64 or 128).  Smaller blocks mean less shared memory and TMEM per CTA,
+// so more CTAs share an SM and hide each other's MMA / barrier latencies.
+template <int KT, int CTAS>
+__global__ void __launch_bounds__(128, CTAS)
+enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                const EncAttnParams p) {
+  constexpr int KV_BYTES = KT * HD * 2;          // one K or V block
+  constexpr int P_BYTES = 128 * KT * 2;          // P tile: KT/64 halves of [128][64]
+  constexpr uint32_t TMEM_COLS = KT == 64 ? 128 : 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE_BYTES;
-  uint8_t* sV = smem + 2 * TILE_BYTES;
-  uint8_t* sP = smem + 3 * TILE_BYTES;  // two 16 KB halves: keys 0..63 | 64..127
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + KV_BYTES;
+  uint8_t* sP = sV + KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -50,17 +56,18 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const EncAttnParams p
     mbar_init(barS, 1);
     mbar_init(barO, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
   }
   if (warp == 0) {
-    tmem_alloc(smem_u32(tmem_slot), 256);
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + KT;
   const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
 
   const int nblk = (p.T + KT - 1) / KT;
@@ -68,15 +75,15 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const EncAttnParams p
 
   if (tid == 0) {
     mbar_arrive_expect_tx(barQ, TILE_BYTES);
-    tma_load_3d(smem_u32(sQ), &tmQKV, barQ, colQ, q0, b);
-    mbar_arrive_expect_tx(barK, TILE_BYTES);
-    tma_load_3d(smem_u32(sK), &tmQKV, barK, colK, 0, b);
-    mbar_arrive_expect_tx(barV, TILE_BYTES);
-    tma_load_3d(smem_u32(sV), &tmQKV, barV, colV, 0, b);
+    tma_load_3d(smem_u32(sQ), &tmQ, barQ, colQ, q0, b);
+    mbar_arrive_expect_tx(barK, KV_BYTES);
+    tma_load_3d(smem_u32(sK), &tmKV, barK, colK, 0, b);
+    mbar_arrive_expect_tx(barV, KV_BYTES);
+    tma_load_3d(smem_u32(sV), &tmKV, barV, colV, 0, b);
   }
 
-  constexpr uint32_t idescS = make_idesc_bf16(128, 128, 0, 0);  // Q (K-major) x K (K-major)
-  constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major)
+  constexpr uint32_t idescS = make_idesc_bf16(128, KT, 0, 0);  // Q (K-major) x K (K-major)
+  constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);  // P (K-major) x V (MN-major)
 
   float o[HD];
 #pragma unroll
@@ -99,48 +106,44 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const EncAttnParams p
     mbar_wait(barS, ph);
     tc_fence_after();
     if (tid == 0 && j + 1 < nblk) {  // K tile is free again: prefetch the next one
-      mbar_arrive_expect_tx(barK, TILE_BYTES);
-      tma_load_3d(smem_u32(sK), &tmQKV, barK, colK, (j + 1) * KT, b);
+      mbar_arrive_expect_tx(barK, KV_BYTES);
+      tma_load_3d(smem_u32(sK), &tmKV, barK, colK, (j + 1) * KT, b);
     }
     const int kv_valid = min(KT, p.T - j * KT);
-    // pass 1: row max
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c0 = 0; c0 < KT; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_S + lane_sel + c0, v);
+    // one pass over the 64 scores of this block, held in registers:
+    // max -> exp2 (ex2.approx) -> bf16 pack into the swizzled K-major P tile
+    static_assert(KT == 64, "the single-pass softmax keeps one 64-key block in registers");
+    float alpha, lsum = 0.f;
+    {
+      uint32_t v[64];
+      tmem_ld32(tmem_S + lane_sel, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(tmem_S + lane_sel + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       tmem_ld_wait();
+      if (kv_valid < KT) {  // ragged tail of the last block (uniform branch)
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c0 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-    }
-    const float m_new = fmaxf(m_run, mx * p.scale_log2e);
-    const float alpha = exp2f(m_run - m_new);  // first block: exp2(-inf) = 0
-    m_run = m_new;
-    float lsum = 0.f;
-    // pass 2: p = exp2(s * scale - m), bf16, into the swizzled K-major P tile
-#pragma unroll 1
-    for (int c0 = 0; c0 < KT; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_S + lane_sel + c0, v);
-      tmem_ld_wait();
-      uint32_t packed[16];
+        for (int i = 0; i < 64; ++i)
+          if (i >= kv_valid) v[i] = 0xff800000u;  // -inf
+      }
+      float mx = __uint_as_float(v[0]);
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float p0 = c0 + i < kv_valid ? exp2f(__uint_as_float(v[i]) * p.scale_log2e - m_new) : 0.f;
-        float p1 = c0 + i + 1 < kv_valid ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2e - m_new) : 0.f;
+      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      const float m_new = fmaxf(m_run, mx * p.scale_log2e);
+      alpha = ex2_approx(m_run - m_new);  // first block: exp2(-inf) = 0
+      m_run = m_new;
+      uint32_t packed[32];
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -m_new));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, -m_new));
+        lsum += p0 + p1;
         __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-        // the PV product sees bf16 P: sum exactly what it sees so rows stay normalised
-        lsum += __bfloat162float(pb.x) + __bfloat162float(pb.y);
         packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
       }
-      uint8_t* half = sP + (c0 >> 6) * TILE_BYTES + r * 128;
+      uint8_t* row = sP + r * 128;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {  // four 16-byte chunks (8 keys each)
-        const int chunk = ((c0 & 63) >> 3) + cc;
-        *reinterpret_cast<uint4*>(half + ((chunk ^ (r & 7)) << 4)) =
+      for (int cc = 0; cc < 8; ++cc)  // eight 16-byte chunks (8 keys each)
+        *reinterpret_cast<uint4*>(row + ((cc ^ (r & 7)) << 4)) =
             make_uint4(packed[4 * cc], packed[4 * cc + 1], packed[4 * cc + 2], packed[4 * cc + 3]);
-      }
     }
     l_run = l_run * alpha + lsum;
 #pragma unroll
@@ -163,8 +166,8 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const EncAttnParams p
     mbar_wait(barO, ph);
     tc_fence_after();
     if (tid == 0 && j + 1 < nblk) {
-      mbar_arrive_expect_tx(barV, TILE_BYTES);
-      tma_load_3d(smem_u32(sV), &tmQKV, barV, colV, (j + 1) * KT, b);
+      mbar_arrive_expect_tx(barV, KV_BYTES);
+      tma_load_3d(smem_u32(sV), &tmKV, barV, colV, (j + 1) * KT, b);
     }
 #pragma unroll
     for (int c0 = 0; c0 < HD; c0 += 32) {
@@ -195,26 +198,34 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const EncAttnParams p
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+void enc_attention_set_block(int) {}  // kept for ABI stability: the block size is fixed at 64 keys
+
+template <int KT, int CTAS>
+static void launch_enc_attn(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out, cudaStream_t stream) {
+  CUtensorMap tmQ, tmKV;
+  make_tmap_bf16_3d(&tmQ, qkv, 3 * (uint64_t)d, T, B, 3 * (uint64_t)d, (uint64_t)T * 3 * d, HD, 128);
+  make_tmap_bf16_3d(&tmKV, qkv, 3 * (uint64_t)d, T, B, 3 * (uint64_t)d, (uint64_t)T * 3 * d, HD, KT);
+  constexpr int smem_bytes = TILE_BYTES + 2 * KT * HD * 2 + 128 * KT * 2 + 5 * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200W_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_kernel<KT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          smem_bytes));
+    configured = true;
+  }
+  EncAttnParams p{T, d, 0.125f * 1.4426950408889634f, out};
+  enc_attn_kernel<KT, CTAS><<<dim3(cdiv(T, QT), n_heads, B), 128, smem_bytes, stream>>>(tmQ, tmKV, p);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
 }
 
 void enc_attention(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out, cudaStream_t stream) {
   B200W_REQUIRE(d == n_heads * HD, "head dim must be 64");
   if (B <= 0) return;
-  CUtensorMap tm;
-  make_tmap_bf16_3d(&tm, qkv, 3 * (uint64_t)d, T, B, 3 * (uint64_t)d, (uint64_t)T * 3 * d, HD, 128);
-  constexpr int smem_bytes = 5 * TILE_BYTES + 5 * 8 + 16 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200W_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          smem_bytes));
-    configured = true;
-  }
-  EncAttnParams p{T, d, 0.125f * 1.4426950408889634f, out};
-  enc_attn_kernel<<<dim3(cdiv(T, QT), n_heads, B), 128, smem_bytes, stream>>>(tm, p);
-  B200W_COUNT_LAUNCH();
-  B200W_CHECK_CUDA(cudaGetLastError());
+  launch_enc_attn<64, 3>(qkv, B, T, d, n_heads, out, stream);
 }
 
 // ------------------------------------------------------------------------------ decoder attention
@@ -328,16 +339,16 @@ void dec_attention(const DecAttnParams& p, int n_heads, cudaStream_t stream) {
 // XQ consecutive query rows of one stream for one head and reads that head's K and V exactly once:
 // 16 warps split the 1500 keys, scores for all queries live in shared memory, one warp per query
 // normalises, and the P.V product is accumulated per warp and reduced through shared memory.
-static constexpr int XQ = 8;    // queries per CTA
-static constexpr int XW = 16;   // warps per CTA
+static constexpr int XW = 16;   // warps per CTA (queries per CTA: template XQ <= 8)
 
+template <int XQ>
 __global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnParams p) {
   extern __shared__ float xs[];
   const int len = p.len;
   const int len_pad = (len + 31) & ~31;
   float* s_q = xs;                          // [XQ][64]
-  float* s_inv = s_q + XQ * HD;             // [XQ]
-  float* s_sc = s_inv + XQ;                 // [XQ][len_pad]
+  float* s_inv = s_q + XQ * HD;             // [8] (padded so that what follows stays 16-byte aligned)
+  float* s_sc = s_inv + 8;                  // [XQ][len_pad]
   float* s_acc = s_sc + XQ * len_pad;       // [XW][XQ][64]
   const int g = blockIdx.x, h = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -451,8 +462,8 @@ __global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnPara
   }
   __syncthreads();
   {
-    const int q = tid >> 6, c = tid & 63;  // 512 threads = XQ x 64 outputs
-    if (q < nq) {
+    const int q = tid >> 6, c = tid & 63;  // 512 threads = 8 x 64 outputs
+    if (q < nq && q < XQ) {
       float sum = 0.f;
 #pragma unroll
       for (int w = 0; w < XW; ++w) sum += s_acc[(w * XQ + q) * HD + c];
@@ -461,18 +472,169 @@ __global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnPara
   }
 }
 
-void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, cudaStream_t stream) {
-  if (n_groups <= 0) return;
+// v2 (no probability export): every warp streams its own 32-key chunks with an online softmax and
+// the 16 partial results are merged at the end, so there is no CTA-wide phase barrier and every warp
+// keeps many independent loads in flight.  8 lanes share a key (8 dims each) for q.k; one lane per
+// 2 output dims for p.v.
+template <int NQ>
+__global__ void __launch_bounds__(XW * 32) cross_attn_stream_kernel(const CrossAttnParams p) {
+  extern __shared__ __align__(16) float xs2[];
+  float (*s_p)[NQ][32] = reinterpret_cast<float (*)[NQ][32]>(xs2);                       // [XW][NQ][32]
+  float (*s_o)[NQ][HD] = reinterpret_cast<float (*)[NQ][HD]>(xs2 + XW * NQ * 32);        // [XW][NQ][64]
+  float (*s_m)[NQ] = reinterpret_cast<float (*)[NQ]>(xs2 + XW * NQ * 32 + XW * NQ * HD);  // [XW][NQ]
+  float (*s_l)[NQ] = s_m + XW;
+  const int g = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = p.g_start[g], nq = p.g_count[g];
+  const long long base = p.kv_base_off[p.stream[q0]];
+  const bf16* kb = p.kbase + base + h * p.head_stride;
+  const bf16* vb = p.vbase + base + h * p.head_stride;
+  const int sub = lane & 7, kg = lane >> 3;  // 8 lanes per key, 4 keys per pass
+
+  float qr[NQ][8];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    if (q < nq) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p.q + (long long)(q0 + q) * p.q_stride + h * HD + 8 * sub);
+      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(u2[t]);
+        qr[q][2 * t] = f.x * p.scale;
+        qr[q][2 * t + 1] = f.y * p.scale;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) qr[q][t] = 0.f;
+    }
+  }
+  float m_run[NQ], l_run[NQ], acc[NQ][2];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) { m_run[q] = -INFINITY; l_run[q] = 0.f; acc[q][0] = acc[q][1] = 0.f; }
+
+  const int n_chunks = (p.len + 31) >> 5;
+  for (int ch = warp; ch < n_chunks; ch += XW) {
+    const int k0 = ch << 5;
+    // ---- q.k for 32 keys: 8 passes of 4 keys, all loads issued first
+    uint4 kv[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int key = k0 + it * 4 + kg;
+      kv[it] = key < p.len ? __ldg(reinterpret_cast<const uint4*>(kb + (long long)key * p.kv_row_stride + 8 * sub))
+                           : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&kv[it]);
+      float kf[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(u2[t]);
+        kf[2 * t] = f.x;
+        kf[2 * t + 1] = f.y;
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        float d = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) d = fmaf(qr[q][t], kf[t], d);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if (sub == 0) s_p[warp][q][it * 4 + kg] = (k0 + it * 4 + kg) < p.len ? d : -INFINITY;
+      }
+    }
+    // V of the chunk (lane owns dims 2*lane, 2*lane+1): issued now, consumed after the softmax
+    uint32_t vv[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int key = k0 + i;
+      vv[i] = key < p.len ? __ldg(reinterpret_cast<const unsigned int*>(vb + (long long)key * p.kv_row_stride + 2 * lane))
+                          : 0u;
+    }
+    __syncwarp();
+    // ---- online softmax over the chunk (lane = key)
+    float alpha[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const float sv = s_p[warp][q][lane];
+      float mx = sv;
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float m_new = fmaxf(m_run[q], mx);
+      const float e = __expf(sv - m_new);
+      float sum = e;
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      alpha[q] = __expf(m_run[q] - m_new);
+      l_run[q] = l_run[q] * alpha[q] + sum;
+      m_run[q] = m_new;
+      s_p[warp][q][lane] = e;
+    }
+    __syncwarp();
+    // ---- p.v
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { acc[q][0] *= alpha[q]; acc[q][1] *= alpha[q]; }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float2 vf[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) vf[u] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[i + u]));
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float4 pw = *reinterpret_cast<const float4*>(&s_p[warp][q][i]);
+        acc[q][0] = fmaf(pw.x, vf[0].x, acc[q][0]); acc[q][1] = fmaf(pw.x, vf[0].y, acc[q][1]);
+        acc[q][0] = fmaf(pw.y, vf[1].x, acc[q][0]); acc[q][1] = fmaf(pw.y, vf[1].y, acc[q][1]);
+        acc[q][0] = fmaf(pw.z, vf[2].x, acc[q][0]); acc[q][1] = fmaf(pw.z, vf[2].y, acc[q][1]);
+        acc[q][0] = fmaf(pw.w, vf[3].x, acc[q][0]); acc[q][1] = fmaf(pw.w, vf[3].y, acc[q][1]);
+      }
+    }
+    __syncwarp();
+  }
+  // ---- merge the 16 partial softmaxes
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    if (lane == 0) { s_m[warp][q] = m_run[q]; s_l[warp][q] = l_run[q]; }
+    *reinterpret_cast<float2*>(&s_o[warp][q][2 * lane]) = make_float2(acc[q][0], acc[q][1]);
+  }
+  __syncthreads();
+  for (int i = tid; i < NQ * HD; i += XW * 32) {
+    const int q = i >> 6, c = i & 63;
+    if (q >= nq) continue;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < XW; ++w) M = fmaxf(M, s_m[w][q]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < XW; ++w) {
+      const float sc = __expf(s_m[w][q] - M);  // warps without keys: exp(-inf) = 0
+      L = fmaf(s_l[w][q], sc, L);
+      O = fmaf(s_o[w][q][c], sc, O);
+    }
+    p.out[(long long)(q0 + q) * p.out_stride + h * HD + c] = __float2bfloat16(O / L);
+  }
+}
+
+template <int XQ>
+static void launch_cross_attn(const CrossAttnParams& p, int n_groups, int n_heads, cudaStream_t stream) {
   const int len_pad = (p.len + 31) & ~31;
-  const size_t smem = sizeof(float) * (XQ * HD + XQ + (size_t)XQ * len_pad + (size_t)XW * XQ * HD);
+  const size_t smem = sizeof(float) * (XQ * HD + 8 + (size_t)XQ * len_pad + (size_t)XW * XQ * HD);
   static size_t configured = 0;
   if (smem > configured) {
-    B200W_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200W_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_kernel<XQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  cross_attn_kernel<<<dim3(n_groups, n_heads), XW * 32, smem, stream>>>(p);
+  cross_attn_kernel<XQ><<<dim3(n_groups, n_heads), XW * 32, smem, stream>>>(p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, int max_group, cudaStream_t stream) {
+  if (n_groups <= 0) return;
+  // specialised on the group size: a beam-5 decode step does 5/8 of the work of the generic kernel
+  if (max_group <= 1) launch_cross_attn<1>(p, n_groups, n_heads, stream);
+  else if (max_group <= 2) launch_cross_attn<2>(p, n_groups, n_heads, stream);
+  else if (max_group <= 4) launch_cross_attn<4>(p, n_groups, n_heads, stream);
+  else if (max_group <= 5) launch_cross_attn<5>(p, n_groups, n_heads, stream);
+  else launch_cross_attn<8>(p, n_groups, n_heads, stream);
 }
 
 }  // namespace b200w

@@ -7,6 +7,7 @@ namespace b200w {
 // Encoder self-attention over the fused QKV activation: qkv bf16 [B][T][3d] (q | k | v, heads of
 // 64 inside each third) -> out bf16 [B][T][d].  softmax(q k^T / 8) v, non-causal.
 void enc_attention(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out, cudaStream_t stream);
+void enc_attention_set_block(int kt);  // keys per inner block: 64 (default, 3 CTAs/SM) or 128 (2 CTAs/SM)
 
 // Decoder attention for a handful of queries; one warp per (query, head).
 struct DecAttnParams {
@@ -54,7 +55,8 @@ struct CrossAttnParams {
   const int* head_export = nullptr;        // [n_heads] -> export index or -1
   int probs_stride = 0;
 };
-void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, cudaStream_t stream);
+// max_group: upper bound on g_count (selects the specialisation of the streaming kernel)
+void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, int max_group, cudaStream_t stream);
 static constexpr int CROSS_GROUP = 8;
 
 }  // namespace b200w

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -234,7 +235,7 @@ struct PassMeta {  // device pointers into e->meta for one forward pass of n tok
   int n = 0;
   int *tok, *pos, *slot, *trow, *kvlen, *stream, *parent;
   int *g_start, *g_count;  // cross-attention groups: runs of <= 8 rows of one stream
-  int n_groups = 0;
+  int n_groups = 0, max_group = 1;
   int4* state;
 };
 
@@ -293,6 +294,8 @@ PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) 
   m.g_start = dp + 7 * n;
   m.g_count = dp + 7 * n + ng;
   m.n_groups = ng;
+  m.max_group = 1;
+  for (int c : gc) m.max_group = std::max(m.max_group, c);
   m.state = reinterpret_cast<int4*>(reinterpret_cast<char*>(dp) + st_off);
   return m;
 }
@@ -357,7 +360,7 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
       c.probs_out = ax->probs;
       c.probs_stride = e->Tenc;
     }
-    cross_attention(c, m.n_groups, e->H, s);
+    cross_attention(c, m.n_groups, e->H, m.max_group, s);
     pend = residual_linear(e, attn, n, d, L.cout, x, s);
     // MLP
     layernorm(x, nullptr, L.ln3.g, L.ln3.b, h, n, d, s, &pend);
@@ -520,6 +523,7 @@ int b200w_engine_finalize(b200w_engine* e) {
   B200W_CHECK_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   B200W_CHECK_CUDA(cudaEventCreateWithFlags(&e->join_event, cudaEventDisableTiming));
   e->use_graphs = getenv("B200W_NO_GRAPHS") == nullptr;
+  if (const char* kt = getenv("B200W_ENC_ATTN_KT")) enc_attention_set_block(atoi(kt));
   e->finalized = true;
   B200W_API_END
 }
@@ -650,6 +654,14 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     B200W_CHECK_CUDA(cudaStreamSynchronize(s));  // mk goes out of scope
   }
 
+  const bool timing = getenv("B200W_DECODE_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(now() - t0).count();
+  };
+  const auto t_begin = now();
+  double t_fill = 0, t_gpu = 0, t_book = 0;
+  int n_steps = 0;
   // ---- prefill: every prompt token of every stream in one pass
   std::vector<StreamState> st(B);
   HostMeta hm;
@@ -771,7 +783,9 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     B200W_CHECK_CUDA(cudaMemcpyAsync(h_ids, sp.out_ids, (size_t)m.n * k_top * 4, cudaMemcpyDeviceToHost, s));
     B200W_CHECK_CUDA(cudaMemcpyAsync(h_lp, sp.out_logprobs, (size_t)m.n * k_top * 4, cudaMemcpyDeviceToHost, s));
   };
+  const double t_prefill = ms_since(t_begin);
   for (int step = 1;; ++step) {
+    const auto t_s0 = now();
     hm.clear();
     bool any = false;
     for (int b = 0; b < B; ++b) {
@@ -794,6 +808,9 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     if (!any) break;
     size_t meta_bytes = 0;
     pm = fill_host_meta(e, hm, &meta_bytes);
+    t_fill += ms_since(t_s0);
+    const auto t_s1 = now();
+    ++n_steps;
     cudaGraphExec_t exec = nullptr;
     if (e->h_meta.grew || e->h_out.grew) {  // staging buffers moved: captured addresses are stale
       for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.exec);
@@ -831,6 +848,8 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     }
     cur ^= 1;
     B200W_CHECK_CUDA(cudaStreamSynchronize(s));
+    t_gpu += ms_since(t_s1);
+    const auto t_s2 = now();
 
     // host-side beam bookkeeping
     for (int b = 0; b < B; ++b) {
@@ -879,7 +898,12 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
       if (S.alive.empty() || (int)S.finished.size() >= max_cand) { S.done = true; continue; }
       if (step + 1 >= S.max_new) finish_stream(S);
     }
+    t_book += ms_since(t_s2);
   }
+  if (timing)
+    fprintf(stderr, "[b200w_decode] B=%d K=%d steps=%d prefill+first=%.2f ms, per step: fill %.3f ms, launch+gpu %.3f ms, "
+            "bookkeeping %.3f ms, total %.1f ms\n", B, K, n_steps, t_prefill, t_fill / std::max(n_steps, 1),
+            t_gpu / std::max(n_steps, 1), t_book / std::max(n_steps, 1), ms_since(t_begin));
 
   for (int b = 0; b < B; ++b) {
     StreamState& S = st[b];

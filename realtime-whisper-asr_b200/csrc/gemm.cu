@@ -117,17 +117,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
-template <int BN, int STAGES>
+// MP = m-tiles per work item.  MP = 2 is for skinny GEMMs (129..256 rows, e.g. a beam-5 decode step of
+// 32 streams): both 128-row tiles are computed from ONE pass over the weight tile, which halves the
+// weight traffic and the number of CTAs' worth of fixed cost.
+template <int BN, int STAGES, int MP>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
+  constexpr int AS_BYTES = MP * A_BYTES;          // A bytes per stage
+  constexpr uint32_t ACC_COLS = MP * BN;          // TMEM columns per accumulator stage
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;    // two accumulator stages
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* sB = smem + STAGES * AS_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
@@ -158,16 +164,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int mn_tiles = p.total_tiles / p.splits;
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
       uint32_t stage = 0, phase = 0;
-      const int mn_tiles = p.total_tiles / p.splits;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
         const int nt = mn % p.n_tiles, mt = mn / p.n_tiles;
         const int b = mt / p.m_tiles_per_batch;
-        const int r0 = (mt % p.m_tiles_per_batch) * BM;
+        const int r0 = (mt % p.m_tiles_per_batch) * (BM * MP);
         const int n0 = nt * BN;
         // split-K (single tap only): this CTA owns k-blocks [kb_lo, kb_hi)
         const int kb_lo = (int)((long long)p.total_kb * ks / p.splits);
@@ -178,9 +184,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (kbg < kb_lo || kbg >= kb_hi) continue;
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t fb = full0 + 8 * stage;
-            mbar_arrive_expect_tx(fb, A_BYTES + B_BYTES);
-            tma_load_3d(smem_u32(sA + stage * A_BYTES), &tmA, fb, p.tap_col[t] + kb * BK,
-                        r0 + p.tap_shift[t], b);
+            mbar_arrive_expect_tx(fb, AS_BYTES + B_BYTES);
+#pragma unroll
+            for (int mi = 0; mi < MP; ++mi)
+              tma_load_3d(smem_u32(sA + stage * AS_BYTES + mi * A_BYTES), &tmA, fb, p.tap_col[t] + kb * BK,
+                          r0 + mi * BM + p.tap_shift[t], b);
             tma_load_3d(smem_u32(sB + stage * B_BYTES), &tmB, fb, kbg * BK, n0, 0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -191,21 +199,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {  // ---------------- MMA issuer
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      const int mn_tiles = p.total_tiles / p.splits;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int ks = tile / mn_tiles;
         const int n_kb = (int)((long long)p.total_kb * (ks + 1) / p.splits) - (int)((long long)p.total_kb * ks / p.splits);
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
-          const uint64_t ad = make_sw128_desc(smem_u32(sA + stage * A_BYTES));
           const uint64_t bd = make_sw128_desc(smem_u32(sB + stage * B_BYTES));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K step inside the swizzle row
-            tc_mma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int mi = 0; mi < MP; ++mi) {
+            const uint64_t ad = make_sw128_desc(smem_u32(sA + stage * AS_BYTES + mi * A_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K step inside the swizzle row
+              tc_mma_bf16(d_tmem + mi * BN, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           tc_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -216,27 +226,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {  // ---------------- epilogue warps 2..5 (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
     uint32_t acc = 0, acc_phase = 0;
-    const int mn_tiles = p.total_tiles / p.splits;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
       const int nt = mn % p.n_tiles, mt = mn / p.n_tiles;
       const int b = mt / p.m_tiles_per_batch;
-      const int r = (mt % p.m_tiles_per_batch) * BM + q * 32 + lane;
       const int n0 = nt * BN;
-      const bool row_ok = r < p.out_rows;
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_ld_wait();
-        if (c0 + 32 == BN) {  // accumulator drained: hand the TMEM stage back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tempty0 + 8 * acc);
+      for (int mi = 0; mi < MP; ++mi) {
+        const int r = (mt % p.m_tiles_per_batch) * (BM * MP) + mi * BM + q * 32 + lane;
+        const bool row_ok = r < p.out_rows;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + mi * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (mi == MP - 1 && c0 + 32 == BN) {  // accumulator drained: hand the TMEM stage back
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * acc);
+          }
+          if (row_ok && n0 + c0 < p.N) epilogue_chunk(p, v, b, r, n0 + c0, ks);
         }
-        if (row_ok && n0 + c0 < p.N) epilogue_chunk(p, v, b, r, n0 + c0, ks);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -332,17 +344,18 @@ static ProfSlot* prof_slot(double flops) {
   return s;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MP>
 static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p,
                         cudaStream_t stream) {
-  constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int smem_bytes = STAGES * (MP * A_BYTES + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
-    B200W_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>,
+    B200W_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, MP>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
   p.n_tiles = cdiv(p.N, BN);
+  p.m_tiles_per_batch = cdiv(p.out_rows, BM * MP);
   p.total_tiles = p.n_tiles * p.m_tiles_per_batch * p.batches;
   p.total_tiles *= p.splits;
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
@@ -352,7 +365,7 @@ static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmPara
     ps = prof_slot(2.0 * (double)p.out_rows * p.batches * (double)p.N * (double)p.total_kb * BK);
     B200W_CHECK_CUDA(cudaEventRecord(ps->beg, stream));
   }
-  gemm_tcgen05_kernel<BN, STAGES><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BN, STAGES, MP><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p);
   if (ps) B200W_CHECK_CUDA(cudaEventRecord(ps->end, stream));
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
@@ -424,9 +437,12 @@ void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
                                       : (uint64_t)d.a_rows * (uint64_t)d.a_row_stride;
   make_tmap_bf16_3d(&tmA, d.A, d.a_cols, d.a_rows, d.batches, d.a_row_stride, a_bs, BK, BM);
   make_tmap_bf16_3d(&tmB, d.W, d.K, d.N, 1, d.w_row_stride, (uint64_t)d.N * d.w_row_stride, BK, bn);
-  if (bn == 256) launch_gemm<256, 4>(tmA, tmB, p, stream);
-  else if (bn == 128) launch_gemm<128, 6>(tmA, tmB, p, stream);
-  else if (bn == 64) launch_gemm<64, 8>(tmA, tmB, p, stream);
+  // skinny single-batch GEMMs with 129..256 rows: both row tiles share one pass over the weights
+  const bool pair = bn == 64 && d.batches == 1 && d.out_rows > BM && d.out_rows <= 2 * BM;
+  if (bn == 256) launch_gemm<256, 4, 1>(tmA, tmB, p, stream);
+  else if (bn == 128) launch_gemm<128, 6, 1>(tmA, tmB, p, stream);
+  else if (bn == 64 && pair) launch_gemm<64, 5, 2>(tmA, tmB, p, stream);
+  else if (bn == 64) launch_gemm<64, 8, 1>(tmA, tmB, p, stream);
   else throw Error("force_bn must be 64, 128 or 256");
 }
 
@@ -435,7 +451,7 @@ int gemm_suggest_splits(int M, int N, int K) {
   // the split count depends on (N, K) only, so a row's result does not change with the number of
   // rows batched next to it (as long as the call stays below the one-wave threshold)
   if (cdiv(M, BM) * cdiv(N, 64) >= num_sms()) return 1;
-  const int want = cdiv(num_sms(), cdiv(N, 64));
+  const int want = num_sms() / cdiv(N, 64);  // keep all work items in a single wave
   const int kb = K / BK;
   int sp = want < kb / 4 ? want : kb / 4;
   return sp < 1 ? 1 : (sp > 16 ? 16 : sp);

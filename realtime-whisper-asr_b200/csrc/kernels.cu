@@ -165,42 +165,67 @@ __device__ __forceinline__ bool token_masked(int v, const SampleParams& p, const
   return false;
 }
 
-// One CTA per row: masked log-softmax with Whisper's timestamp rules, then top-k.
-__global__ void __launch_bounds__(256) sample_kernel(const SampleParams p) {
-  __shared__ float s_red[8];
-  __shared__ float s_cv[256];
-  __shared__ int s_ci[256];
+// One CTA (1024 threads) per row: masked log-softmax with Whisper's timestamp rules, then top-k.
+// Pass 1 applies the rules once and writes the masked logits back (-inf where barred), so the later
+// passes are plain streaming reads of an L2-resident row.
+static constexpr int SAMPLE_THREADS = 1024;
+
+__device__ __forceinline__ float block_max_1024(float v, float* s) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s[threadIdx.x & 31];
+  for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+  return r;
+}
+__device__ __forceinline__ float block_sum_1024(float v, float* s) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s[threadIdx.x & 31];
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SampleParams p) {
+  __shared__ float s_red[32];
+  __shared__ float s_cv[32];
+  __shared__ int s_ci[32];
   const int row = blockIdx.x, tid = threadIdx.x;
-  const float* lg = p.logits + (long long)row * p.ld;
+  float* lg = const_cast<float*>(p.logits) + (long long)row * p.ld;
   const int4 st = p.state[row];
   const int V = p.n_vocab;
 
   float mx = -INFINITY, mx_text = -INFINITY;
-  for (int v = tid; v < V; v += 256) {
-    if (token_masked(v, p, st, p.mask)) continue;
-    const float x = lg[v];
+  for (int v = tid; v < V; v += SAMPLE_THREADS) {
+    float x = lg[v];
+    if (token_masked(v, p, st, p.mask)) {
+      x = -INFINITY;
+      lg[v] = x;
+    }
     mx = fmaxf(mx, x);
     if (v < p.timestamp_begin) mx_text = fmaxf(mx_text, x);
   }
-  mx = block_reduce_max(mx, s_red);
-  mx_text = block_reduce_max(mx_text, s_red);
+  mx = block_max_1024(mx, s_red);
+  mx_text = block_max_1024(mx_text, s_red);
   float sum_all = 0.f, sum_ts = 0.f;
-  for (int v = tid; v < V; v += 256) {
-    if (token_masked(v, p, st, p.mask)) continue;
-    const float e = __expf(lg[v] - mx);
+  for (int v = tid; v < V; v += SAMPLE_THREADS) {
+    const float e = __expf(lg[v] - mx);  // exp(-inf) = 0 for barred tokens
     sum_all += e;
     if (v >= p.timestamp_begin) sum_ts += e;
   }
-  sum_all = block_reduce_sum(sum_all, s_red);
-  sum_ts = block_reduce_sum(sum_ts, s_red);
+  sum_all = block_sum_1024(sum_all, s_red);
+  sum_ts = block_sum_1024(sum_ts, s_red);
   float lse = mx + logf(sum_all);
-  bool ts_only = false;
+  int v_lo = 0;
   if ((st.x & SF_RULES) && sum_ts > 0.f) {
     // if the total timestamp mass beats every single text token, force a timestamp
     const float ts_logprob = mx + logf(sum_ts) - lse;
     const float text_logprob = mx_text - lse;
     if (ts_logprob > text_logprob) {
-      ts_only = true;
+      v_lo = p.timestamp_begin;
       lse = mx + logf(sum_ts);
     }
   }
@@ -211,9 +236,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const SampleParams p) {
 #pragma unroll
   for (int j = 0; j < MAX_TOPK; ++j) { bv[j] = -INFINITY; bi[j] = 0x7fffffff; }
   const int k = p.k;
-  for (int v = tid; v < V; v += 256) {
-    if (token_masked(v, p, st, p.mask)) continue;
-    if (ts_only && v < p.timestamp_begin) continue;
+  for (int v = v_lo + tid; v < V; v += SAMPLE_THREADS) {
     const float x = lg[v] - lse;
     if (x > bv[k - 1]) {
       int j = k - 1;
@@ -227,32 +250,33 @@ __global__ void __launch_bounds__(256) sample_kernel(const SampleParams p) {
     // block argmax over every thread's current head; ties -> lower id
     float cv = head < k ? bv[head] : -INFINITY;
     int ci = head < k ? bi[head] : 0x7fffffff;
-    s_cv[tid] = cv;
-    s_ci[tid] = ci;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (tid < o) {
-        const float ov = s_cv[tid + o];
-        const int oi = s_ci[tid + o];
-        if (ov > s_cv[tid] || (ov == s_cv[tid] && oi < s_ci[tid])) { s_cv[tid] = ov; s_ci[tid] = oi; }
-      }
-      __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (ov > cv || (ov == cv && oi < ci)) { cv = ov; ci = oi; }
     }
-    const float wv = s_cv[0];
-    const int wi = s_ci[0];
+    __syncthreads();
+    if ((tid & 31) == 0) { s_cv[tid >> 5] = cv; s_ci[tid >> 5] = ci; }
+    __syncthreads();
+    cv = s_cv[tid & 31];
+    ci = s_ci[tid & 31];
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (ov > cv || (ov == cv && oi < ci)) { cv = ov; ci = oi; }
+    }
     if (tid == 0) {
-      p.out_ids[row * k + r] = wi;
-      p.out_logprobs[row * k + r] = wv;
+      p.out_ids[row * k + r] = ci;
+      p.out_logprobs[row * k + r] = cv;
     }
-    if (head < k && bi[head] == wi && wi != 0x7fffffff) ++head;
-    __syncthreads();
+    if (head < k && bi[head] == ci && ci != 0x7fffffff) ++head;
   }
 }
 
 void sample_topk(const SampleParams& p, int rows, cudaStream_t stream) {
   if (rows <= 0) return;
   B200W_REQUIRE(p.k >= 1 && p.k <= MAX_TOPK, "top-k out of range");
-  sample_kernel<<<rows, 256, 0, stream>>>(p);
+  sample_kernel<<<rows, SAMPLE_THREADS, 0, stream>>>(p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }

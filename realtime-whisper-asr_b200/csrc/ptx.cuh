@@ -150,8 +150,24 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exact-erf GELU, erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution):
+// ~16 instructions instead of erff's ~40, which matters in the fc1 epilogue (4 warps per SM).
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = ex2_approx(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
 }  // namespace b200w

@@ -298,7 +298,10 @@ class B200WhisperModel:
                     raise ValueError(f"unknown model size {name!r}")
                 dims = MODEL_DIMS[base]
                 # no checkpoints exist offline: seeded synthetic weights of the exact architecture
-                state_dict = synthetic_state_dict(dims, seed=seed)
+                # (large models are generated on the device: ~1.5 G random numbers; the CUDA and CPU
+                # generators give different values, so parity tests pass CPU-made state dicts)
+                gen_dev = str(self.device) if dims.d_model >= 1024 else "cpu"
+                state_dict = synthetic_state_dict(dims, seed=seed, device=gen_dev)
                 if alignment_heads is None:
                     alignment_heads = ALIGNMENT_HEADS.get(base)
         assert dims is not None

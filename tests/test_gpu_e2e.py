@@ -72,7 +72,10 @@ def test_greedy_tokens_match_oracle_through_the_backend(model):
         segs = asr.transcribe(audio)
         mel = OF.pad_or_trim(OF.log_mel(audio, md.n_mels)[:, :3000])
         enc = orc.encode(torch.from_numpy(mel[None]))
-        ref = OD.decode_one(orc, enc[0], tk.sot_sequence, opts).tokens
+        # init_prompt="" reaches faster-whisper as initial_prompt="" -> " " is tokenised and sent as
+        # previous text, so the decoder prompt is <|startofprev|> " " <|sot|> <|en|> <|transcribe|>
+        prompt = [tk.sot_prev] + tk.encode(" ") + tk.sot_sequence
+        ref = OD.decode_one(orc, enc[0], prompt, opts).tokens
 
         def is_slice(toks, seq, start=0):
             k = len(toks)
@@ -108,8 +111,8 @@ def test_batch_invariance_and_multi_window(model):
         assert abs(info_b.duration - len(a) / 16000) < 1e-6
     long_segs = batch[4][0]
     assert long_segs[-1].end > 30.0 and max(s.seek for s in long_segs) >= 2000  # several windows were decoded
-    starts = [s.start for s in long_segs]
-    assert starts == sorted(starts)
+    # (no ordering claim across windows: the synthetic model ignores the audio, so a window's
+    # first word may start before the previous window's last segment ended)
 
 
 def test_language_detection_and_info(model):
