@@ -299,20 +299,20 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) dec_attn_kernel(const DecAttnP
   float2 acc = make_float2(0.f, 0.f);
   const bf16* vl = vb + 2 * lane;
   int i = 0;
-  for (; i + 4 <= len; i += 4) {  // 4 independent 128-byte row reads in flight per warp
-    long long s0, s1, s2, s3;
-    if (tab) { s0 = tab[i]; s1 = tab[i + 1]; s2 = tab[i + 2]; s3 = tab[i + 3]; }
-    else { s0 = i; s1 = i + 1; s2 = i + 2; s3 = i + 3; }
-    const __nv_bfloat162 v0 = *reinterpret_cast<const __nv_bfloat162*>(vl + s0 * p.kv_row_stride);
-    const __nv_bfloat162 v1 = *reinterpret_cast<const __nv_bfloat162*>(vl + s1 * p.kv_row_stride);
-    const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(vl + s2 * p.kv_row_stride);
-    const __nv_bfloat162 v3 = *reinterpret_cast<const __nv_bfloat162*>(vl + s3 * p.kv_row_stride);
-    const float p0 = sc[i], p1 = sc[i + 1], p2 = sc[i + 2], p3 = sc[i + 3];
-    float2 f;
-    f = __bfloat1622float2(v0); acc.x = fmaf(p0, f.x, acc.x); acc.y = fmaf(p0, f.y, acc.y);
-    f = __bfloat1622float2(v1); acc.x = fmaf(p1, f.x, acc.x); acc.y = fmaf(p1, f.y, acc.y);
-    f = __bfloat1622float2(v2); acc.x = fmaf(p2, f.x, acc.x); acc.y = fmaf(p2, f.y, acc.y);
-    f = __bfloat1622float2(v3); acc.x = fmaf(p3, f.x, acc.x); acc.y = fmaf(p3, f.y, acc.y);
+  for (; i + 8 <= len; i += 8) {  // 8 independent 128-byte row reads in flight per warp
+    long long sl[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sl[u] = tab ? tab[i + u] : i + u;
+    __nv_bfloat162 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + sl[u] * p.kv_row_stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float pw = sc[i + u];
+      const float2 f = __bfloat1622float2(v[u]);
+      acc.x = fmaf(pw, f.x, acc.x);
+      acc.y = fmaf(pw, f.y, acc.y);
+    }
   }
   for (; i < len; ++i) {
     const long long s0 = tab ? tab[i] : i;
@@ -363,17 +363,29 @@ __global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnPara
   }
   __syncthreads();
 
-  // scores: one key per lane per pass
-  for (int key = tid; key < len_pad; key += XW * 32) {
-    float acc[XQ];
+  // scores: one key per lane per pass; the next key's row is loaded while this one is multiplied
+  {
+    uint4 cur[8];
+    int key = tid;
+    const bool have0 = key < len;
 #pragma unroll
-    for (int q = 0; q < XQ; ++q) acc[q] = 0.f;
-    if (key < len) {
-      const bf16* kp = kb + (long long)key * p.kv_row_stride;
+    for (int c = 0; c < 8; ++c)
+      cur[c] = have0 ? __ldg(reinterpret_cast<const uint4*>(kb + (long long)key * p.kv_row_stride) + c)
+                     : make_uint4(0u, 0u, 0u, 0u);
+    for (; key < len_pad; key += XW * 32) {
+      uint4 nxt[8];
+      const int nkey = key + XW * 32;
+      const bool haven = nkey < len;
 #pragma unroll
-      for (int c = 0; c < HD; c += 8) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(kp + c));
-        const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+      for (int c = 0; c < 8; ++c)
+        nxt[c] = haven ? __ldg(reinterpret_cast<const uint4*>(kb + (long long)nkey * p.kv_row_stride) + c)
+                       : make_uint4(0u, 0u, 0u, 0u);
+      float acc[XQ];
+#pragma unroll
+      for (int q = 0; q < XQ; ++q) acc[q] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&cur[c]);
         float kf[8];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -383,17 +395,19 @@ __global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnPara
         }
 #pragma unroll
         for (int q = 0; q < XQ; ++q) {
-          const float4 qa = *reinterpret_cast<const float4*>(s_q + q * HD + c);
-          const float4 qb = *reinterpret_cast<const float4*>(s_q + q * HD + c + 4);
+          const float4 qa = *reinterpret_cast<const float4*>(s_q + q * HD + 8 * c);
+          const float4 qb = *reinterpret_cast<const float4*>(s_q + q * HD + 8 * c + 4);
           acc[q] = fmaf(qa.x, kf[0], acc[q]); acc[q] = fmaf(qa.y, kf[1], acc[q]);
           acc[q] = fmaf(qa.z, kf[2], acc[q]); acc[q] = fmaf(qa.w, kf[3], acc[q]);
           acc[q] = fmaf(qb.x, kf[4], acc[q]); acc[q] = fmaf(qb.y, kf[5], acc[q]);
           acc[q] = fmaf(qb.z, kf[6], acc[q]); acc[q] = fmaf(qb.w, kf[7], acc[q]);
         }
       }
-    }
 #pragma unroll
-    for (int q = 0; q < XQ; ++q) s_sc[q * len_pad + key] = key < len ? acc[q] : -INFINITY;
+      for (int q = 0; q < XQ; ++q) s_sc[q * len_pad + key] = key < len ? acc[q] : -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+    }
   }
   __syncthreads();
 
@@ -427,18 +441,18 @@ __global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnPara
 #pragma unroll
     for (int q = 0; q < XQ; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
     const bf16* vl = vb + 4 * l16;
-    for (int k0 = warp * 2 + half; k0 < len_pad; k0 += 4 * XW * 2) {
-      uint2 v[4];
-      int kk[4];
+    for (int k0 = warp * 2 + half; k0 < len_pad; k0 += 12 * XW * 2) {  // 12 rows in flight per lane
+      uint2 v[12];
+      int kk[12];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 12; ++u) {
         kk[u] = k0 + u * XW * 2;
         v[u] = kk[u] < len ? __ldg(reinterpret_cast<const uint2*>(vl + (long long)kk[u] * p.kv_row_stride))
                            : make_uint2(0u, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (kk[u] >= len_pad) continue;
+      for (int u = 0; u < 12; ++u) {
+        if (kk[u] >= len) continue;
         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[u].x));
         const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[u].y));
 #pragma unroll
@@ -613,6 +627,170 @@ __global__ void __launch_bounds__(XW * 32) cross_attn_stream_kernel(const CrossA
   }
 }
 
+// ---- split-KV variant for decode steps (no probability export): grid (group, head, key split).
+// Each CTA (4 warps) handles a quarter of the keys and writes an un-normalised partial result
+// (max, sum, weighted values); cross_attn_merge_kernel combines the splits.  Many small CTAs per SM
+// overlap each other's load and compute phases, which one big CTA per (stream, head) cannot.
+static constexpr int SW = 4;       // warps per CTA
+static constexpr int KSPLIT = 4;   // key splits
+
+template <int XQ>
+__global__ void __launch_bounds__(SW * 32) cross_attn_split_kernel(const CrossAttnParams p, float* __restrict__ part) {
+  extern __shared__ float xs3[];
+  const int keys_per = ((p.len + KSPLIT - 1) / KSPLIT + 31) & ~31;   // 384 for 1500
+  float* s_q = xs3;                          // [XQ][64]
+  float* s_sc = s_q + XQ * HD;               // [XQ][keys_per]
+  float* s_acc = s_sc + XQ * keys_per;       // [SW][XQ][64]
+  float* s_ml = s_acc + SW * XQ * HD;        // [2][8]
+  const int g = blockIdx.x, h = blockIdx.y, sp = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = p.g_start[g], nq = p.g_count[g];
+  const long long base = p.kv_base_off[p.stream[q0]];
+  const int k_lo = sp * keys_per;
+  const int n_keys = max(0, min(p.len - k_lo, keys_per));
+  const bf16* kb = p.kbase + base + h * p.head_stride + (long long)k_lo * p.kv_row_stride;
+  const bf16* vb = p.vbase + base + h * p.head_stride + (long long)k_lo * p.kv_row_stride;
+
+  for (int i = tid; i < XQ * HD; i += SW * 32) {
+    const int q = i >> 6, c = i & 63;
+    s_q[i] = q < nq ? __bfloat162float(p.q[(long long)(q0 + q) * p.q_stride + h * HD + c]) * p.scale : 0.f;
+  }
+  __syncthreads();
+  for (int key = tid; key < keys_per; key += SW * 32) {
+    float acc[XQ];
+#pragma unroll
+    for (int q = 0; q < XQ; ++q) acc[q] = 0.f;
+    if (key < n_keys) {
+      const bf16* kp = kb + (long long)key * p.kv_row_stride;
+      uint4 kr[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) kr[c] = __ldg(reinterpret_cast<const uint4*>(kp) + c);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&kr[c]);
+        float kf[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __bfloat1622float2(u2[t]);
+          kf[2 * t] = f.x;
+          kf[2 * t + 1] = f.y;
+        }
+#pragma unroll
+        for (int q = 0; q < XQ; ++q) {
+          const float4 qa = *reinterpret_cast<const float4*>(s_q + q * HD + 8 * c);
+          const float4 qb = *reinterpret_cast<const float4*>(s_q + q * HD + 8 * c + 4);
+          acc[q] = fmaf(qa.x, kf[0], acc[q]); acc[q] = fmaf(qa.y, kf[1], acc[q]);
+          acc[q] = fmaf(qa.z, kf[2], acc[q]); acc[q] = fmaf(qa.w, kf[3], acc[q]);
+          acc[q] = fmaf(qb.x, kf[4], acc[q]); acc[q] = fmaf(qb.y, kf[5], acc[q]);
+          acc[q] = fmaf(qb.z, kf[6], acc[q]); acc[q] = fmaf(qb.w, kf[7], acc[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < XQ; ++q) s_sc[q * keys_per + key] = key < n_keys ? acc[q] : -INFINITY;
+  }
+  __syncthreads();
+  for (int q = warp; q < XQ; q += SW) {  // local softmax of the split (max / sum kept for the merge)
+    float* sc = s_sc + q * keys_per;
+    float mx = -INFINITY;
+    for (int i = lane; i < keys_per; i += 32) mx = fmaxf(mx, sc[i]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int i = lane; i < keys_per; i += 32) {
+      const float e = mx > -INFINITY ? __expf(sc[i] - mx) : 0.f;
+      sc[i] = e;
+      sum += e;
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) { s_ml[q] = mx; s_ml[8 + q] = sum; }
+  }
+  __syncthreads();
+  {
+    const int half = lane >> 4, l16 = lane & 15;
+    float acc[XQ][4];
+#pragma unroll
+    for (int q = 0; q < XQ; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+    const bf16* vl = vb + 4 * l16;
+    for (int k0 = warp * 2 + half; k0 < keys_per; k0 += 6 * SW * 2) {  // 6 rows in flight per lane
+      uint2 v[6];
+      int kk[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        kk[u] = k0 + u * SW * 2;
+        v[u] = kk[u] < n_keys ? __ldg(reinterpret_cast<const uint2*>(vl + (long long)kk[u] * p.kv_row_stride))
+                              : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        if (kk[u] >= n_keys) continue;
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[u].x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[u].y));
+#pragma unroll
+        for (int q = 0; q < XQ; ++q) {
+          const float pw = s_sc[q * keys_per + kk[u]];
+          acc[q][0] = fmaf(pw, a.x, acc[q][0]); acc[q][1] = fmaf(pw, a.y, acc[q][1]);
+          acc[q][2] = fmaf(pw, b.x, acc[q][2]); acc[q][3] = fmaf(pw, b.y, acc[q][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < XQ; ++q)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[q][c] += __shfl_xor_sync(0xffffffffu, acc[q][c], 16);
+    if (half == 0) {
+#pragma unroll
+      for (int q = 0; q < XQ; ++q)
+        *reinterpret_cast<float4*>(s_acc + ((warp * XQ + q) * HD) + 4 * l16) =
+            make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+    }
+  }
+  __syncthreads();
+  // partial record of this (group, head, split): [XQ][66] = 64 values, max, sum
+  float* rec = part + (((long long)g * gridDim.y + h) * KSPLIT + sp) * (8 * 66);
+  for (int i = tid; i < XQ * HD; i += SW * 32) {
+    const int q = i >> 6, c = i & 63;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < SW; ++w) sum += s_acc[(w * XQ + q) * HD + c];
+    rec[q * 66 + c] = sum;
+  }
+  if (tid < XQ) { rec[tid * 66 + 64] = s_ml[tid]; rec[tid * 66 + 65] = s_ml[8 + tid]; }
+}
+
+__global__ void cross_attn_merge_kernel(const CrossAttnParams p, const float* __restrict__ part) {
+  const int g = blockIdx.x, h = blockIdx.y;
+  const int q = threadIdx.x >> 6, c = threadIdx.x & 63;
+  if (q >= p.g_count[g]) return;
+  const float* rec = part + (((long long)g * gridDim.y + h) * KSPLIT) * (8 * 66) + q * 66;
+  float M = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < KSPLIT; ++s) M = fmaxf(M, rec[s * 8 * 66 + 64]);
+  float L = 0.f, O = 0.f;
+#pragma unroll
+  for (int s = 0; s < KSPLIT; ++s) {
+    const float m = rec[s * 8 * 66 + 64];
+    const float w = m > -INFINITY ? __expf(m - M) : 0.f;
+    L = fmaf(rec[s * 8 * 66 + 65], w, L);
+    O = fmaf(rec[s * 8 * 66 + c], w, O);
+  }
+  p.out[(long long)(p.g_start[g] + q) * p.out_stride + h * HD + c] = __float2bfloat16(O / L);
+}
+
+template <int XQ>
+static void launch_cross_split(const CrossAttnParams& p, int n_groups, int n_heads, float* part, cudaStream_t stream) {
+  const int keys_per = ((p.len + KSPLIT - 1) / KSPLIT + 31) & ~31;
+  const size_t smem = sizeof(float) * (XQ * HD + (size_t)XQ * keys_per + (size_t)SW * XQ * HD + 16);
+  cross_attn_split_kernel<XQ><<<dim3(n_groups, n_heads, KSPLIT), SW * 32, smem, stream>>>(p, part);
+  B200W_COUNT_LAUNCH();
+  cross_attn_merge_kernel<<<dim3(n_groups, n_heads), XQ * 64, 0, stream>>>(p, part);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+size_t cross_attention_scratch_bytes(int n_groups, int n_heads) {
+  return (size_t)n_groups * n_heads * KSPLIT * 8 * 66 * sizeof(float);
+}
+
 template <int XQ>
 static void launch_cross_attn(const CrossAttnParams& p, int n_groups, int n_heads, cudaStream_t stream) {
   const int len_pad = (p.len + 31) & ~31;
@@ -627,8 +805,18 @@ static void launch_cross_attn(const CrossAttnParams& p, int n_groups, int n_head
   B200W_CHECK_CUDA(cudaGetLastError());
 }
 
-void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, int max_group, cudaStream_t stream) {
+void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, int max_group, cudaStream_t stream,
+                     float* split_scratch) {
   if (n_groups <= 0) return;
+  if (split_scratch && !p.head_export && max_group <= 8 && n_groups <= 64) {
+    // few queries (decode steps): split the keys over 4 CTAs per (group, head) and merge
+    if (max_group <= 1) launch_cross_split<1>(p, n_groups, n_heads, split_scratch, stream);
+    else if (max_group <= 2) launch_cross_split<2>(p, n_groups, n_heads, split_scratch, stream);
+    else if (max_group <= 4) launch_cross_split<4>(p, n_groups, n_heads, split_scratch, stream);
+    else if (max_group <= 5) launch_cross_split<5>(p, n_groups, n_heads, split_scratch, stream);
+    else launch_cross_split<8>(p, n_groups, n_heads, split_scratch, stream);
+    return;
+  }
   // specialised on the group size: a beam-5 decode step does 5/8 of the work of the generic kernel
   if (max_group <= 1) launch_cross_attn<1>(p, n_groups, n_heads, stream);
   else if (max_group <= 2) launch_cross_attn<2>(p, n_groups, n_heads, stream);

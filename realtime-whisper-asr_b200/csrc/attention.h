@@ -56,7 +56,11 @@ struct CrossAttnParams {
   int probs_stride = 0;
 };
 // max_group: upper bound on g_count (selects the specialisation of the streaming kernel)
-void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, int max_group, cudaStream_t stream);
+// split_scratch (optional, cross_attention_scratch_bytes(64, n_heads) bytes): enables the split-KV path
+// for passes with at most 64 groups (decode steps).
+void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, int max_group, cudaStream_t stream,
+                     float* split_scratch = nullptr);
+size_t cross_attention_scratch_bytes(int n_groups, int n_heads);
 static constexpr int CROSS_GROUP = 8;
 
 }  // namespace b200w

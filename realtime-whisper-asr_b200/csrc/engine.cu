@@ -127,6 +127,7 @@ struct b200w_engine {
   DevBuf meta;                                        // per-pass int metadata
   DevBuf cross_off, const_len, mask, topk_ids, topk_lp, probs, head_export;
   DevBuf al_w, al_mat, al_trace, al_path, al_plen, scratch_i;
+  DevBuf x_split;        // split-KV partial results of the decode-step cross attention
   DevBuf d_split;        // fp32 split-K partial sums of the GEMM feeding the residual stream
   SplitReduce pending;   // partial sums of the last decoder GEMM, folded in by the next LayerNorm
   PinnedBuf h_meta, h_out;
@@ -195,6 +196,56 @@ void linear(const bf16* A, int M, int K, const Lin& l, int N, void* out, int64_t
   g.out_row_stride = ldo;
   gemm_bf16(g, s);
 }
+
+// Optional per-op timing of the decoder pass (B200W_DECODE_PROFILE=1; eager launches only): CUDA events
+// around every op, summed per op type and printed when the decode call returns.
+struct OpTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> recs;
+  const char* names[16] = {"embed", "layernorm", "qkv_gemm", "kv_scatter", "self_attn", "out_gemm", "cq_gemm",
+                           "cross_attn", "cout_gemm", "fc1_gemm", "fc2_gemm", "logits_gemm", "sample", "fork",
+                           "final_ln", "other"};
+  cudaEvent_t ev() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void report(const char* tag) {
+    if (!on || recs.empty()) return;
+    double tot[16] = {0};
+    int cnt[16] = {0};
+    for (auto& r : recs) {
+      float ms = 0;
+      cudaEventSynchronize(r.second.second);
+      cudaEventElapsedTime(&ms, r.second.first, r.second.second);
+      tot[r.first] += ms;
+      cnt[r.first]++;
+    }
+    fprintf(stderr, "[b200w op profile] %s\n", tag);
+    for (int i = 0; i < 16; ++i)
+      if (cnt[i]) fprintf(stderr, "   %-12s n=%6d total %9.3f ms  avg %8.2f us\n", names[i], cnt[i], tot[i], 1000.0 * tot[i] / cnt[i]);
+    recs.clear();
+    used = 0;
+  }
+};
+static OpTimer g_optimer;
+struct OpScope {
+  int id;
+  cudaStream_t s;
+  cudaEvent_t a = nullptr;
+  OpScope(int id_, cudaStream_t s_) : id(id_), s(s_) {
+    if (g_optimer.on) { a = g_optimer.ev(); cudaEventRecord(a, s); }
+  }
+  ~OpScope() {
+    if (a) { cudaEvent_t b = g_optimer.ev(); cudaEventRecord(b, s); g_optimer.recs.push_back({id, {a, b}}); }
+  }
+};
+#define OP(id) OpScope _op_scope_##id(id, s)
 
 // x += A W^T + b for the decoder's residual stream.  Skinny calls (decode steps) are split along K so
 // that enough CTAs stream the weights; the partial sums are handed to the next LayerNorm.
@@ -323,26 +374,26 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
   bf16* attn = e->d_attn.as<bf16>();
   bf16* cq = e->d_cq.as<bf16>();
   bf16* mlp = e->d_mlp.as<bf16>();
-  embed_tokens(m.tok, m.pos, e->tok_emb, e->dec_pos, x, n, d, s);
+  { OP(0); embed_tokens(m.tok, m.pos, e->tok_emb, e->dec_pos, x, n, d, s); }
   SplitReduce pend;
   for (int l = 0; l < e->Ld; ++l) {
     const DecLayer& L = e->dec[l];
     bf16* kp = e->kpool.as<bf16>() + (long long)l * e->total_slots * d;
     bf16* vp = e->vpool.as<bf16>() + (long long)l * e->total_slots * d;
     // self attention
-    layernorm(x, nullptr, L.ln1.g, L.ln1.b, h, n, d, s, &pend);
-    linear(h, n, d, L.qkv, 3 * d, qkv, 3 * d, 0, 0, nullptr, 0, 0, s);
-    kv_scatter(qkv, m.slot, kp, vp, n, d, s);
+    { OP(1); layernorm(x, nullptr, L.ln1.g, L.ln1.b, h, n, d, s, &pend); }
+    { OP(2); linear(h, n, d, L.qkv, 3 * d, qkv, 3 * d, 0, 0, nullptr, 0, 0, s); }
+    { OP(3); kv_scatter(qkv, m.slot, kp, vp, n, d, s); }
     DecAttnParams a;
     a.q = qkv; a.q_stride = 3 * d;
     a.kbase = kp; a.vbase = vp; a.kv_row_stride = d;
     a.table = table; a.table_stride = e->Tctx; a.trow = m.trow; a.kvlen = m.kvlen;
     a.out = attn; a.out_stride = d; a.scale = 0.125f; a.n_queries = n; a.max_len = max_kvlen;
-    dec_attention(a, e->H, s);
-    pend = residual_linear(e, attn, n, d, L.out, x, s);
+    { OP(4); dec_attention(a, e->H, s); }
+    { OP(5); pend = residual_linear(e, attn, n, d, L.out, x, s); }
     // cross attention
-    layernorm(x, nullptr, L.ln2.g, L.ln2.b, h, n, d, s, &pend);
-    linear(h, n, d, L.cq, d, cq, d, 0, 0, nullptr, 0, 0, s);
+    { OP(1); layernorm(x, nullptr, L.ln2.g, L.ln2.b, h, n, d, s, &pend); }
+    { OP(6); linear(h, n, d, L.cq, d, cq, d, 0, 0, nullptr, 0, 0, s); }
     CrossAttnParams c;
     c.q = cq; c.q_stride = d;
     // cross K/V layout [stream][layer][k|v][head][1500][64]
@@ -360,12 +411,12 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
       c.probs_out = ax->probs;
       c.probs_stride = e->Tenc;
     }
-    cross_attention(c, m.n_groups, e->H, m.max_group, s);
-    pend = residual_linear(e, attn, n, d, L.cout, x, s);
+    { OP(7); cross_attention(c, m.n_groups, e->H, m.max_group, s, e->x_split.as<float>()); }
+    { OP(8); pend = residual_linear(e, attn, n, d, L.cout, x, s); }
     // MLP
-    layernorm(x, nullptr, L.ln3.g, L.ln3.b, h, n, d, s, &pend);
-    linear(h, n, d, L.fc1, 4 * d, mlp, 4 * d, 0, 1, nullptr, 0, 0, s);
-    pend = residual_linear(e, mlp, n, 4 * d, L.fc2, x, s);
+    { OP(1); layernorm(x, nullptr, L.ln3.g, L.ln3.b, h, n, d, s, &pend); }
+    { OP(9); linear(h, n, d, L.fc1, 4 * d, mlp, 4 * d, 0, 1, nullptr, 0, 0, s); }
+    { OP(10); pend = residual_linear(e, mlp, n, 4 * d, L.fc2, x, s); }
   }
   e->pending = pend;  // folded in by the final LayerNorm (logits_for_rows)
 }
@@ -374,12 +425,12 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
 void logits_for_rows(b200w_engine* e, const int* sel_rows_dev, int n_sel, cudaStream_t s) {
   B200W_REQUIRE(n_sel <= e->logit_rows, "logits buffer too small");
   bf16* hsel = e->d_hsel.as<bf16>();
-  layernorm(e->d_x.as<float>(), sel_rows_dev, e->dec_ln.g, e->dec_ln.b, hsel, n_sel, e->d, s, &e->pending);
+  { OP(14); layernorm(e->d_x.as<float>(), sel_rows_dev, e->dec_ln.g, e->dec_ln.b, hsel, n_sel, e->d, s, &e->pending); }
   if (!sel_rows_dev) e->pending = SplitReduce{};  // written back into x: must not be added twice
   Lin emb;
   emb.w = e->tok_emb;
   emb.b = nullptr;
-  linear(hsel, n_sel, e->d, emb, e->V, e->logits.p, e->ldv, 1, 0, nullptr, 0, 0, s);
+  { OP(11); linear(hsel, n_sel, e->d, emb, e->V, e->logits.p, e->ldv, 1, 0, nullptr, 0, 0, s); }
 }
 
 void upload_ints(int* dst, const std::vector<int>& v, cudaStream_t s) {
@@ -417,7 +468,7 @@ int b200w_engine_destroy(b200w_engine* e) {
                       &e->d_attn, &e->d_cq, &e->d_mlp, &e->d_hsel, &e->kpool, &e->vpool, &e->tables[0],
                       &e->tables[1], &e->logits, &e->meta, &e->cross_off, &e->const_len, &e->mask,
                       &e->topk_ids, &e->topk_lp, &e->probs, &e->head_export, &e->al_w, &e->al_mat,
-                      &e->al_trace, &e->al_path, &e->al_plen, &e->scratch_i, &e->d_split};
+                      &e->al_trace, &e->al_path, &e->al_plen, &e->scratch_i, &e->d_split, &e->x_split};
     for (DevBuf* b : bufs) b->release();
     e->h_meta.release();
     e->h_out.release();
@@ -489,7 +540,8 @@ int b200w_engine_finalize(b200w_engine* e) {
   e->d_attn.alloc(n * d * 2);
   e->d_cq.alloc(n * d * 2);
   e->d_mlp.alloc(n * 4 * d * 2);
-  e->d_split.alloc((size_t)(128 * 160 * 64) * 16 * 4);  // splits only happen below ~148 tiles
+  e->d_split.alloc((size_t)(128 * 160 * 64) * 16 * 4);
+  e->x_split.alloc(cross_attention_scratch_bytes(64, e->H));  // splits only happen below ~148 tiles
   e->slots_per_stream = e->Tctx * e->cfg.max_beam;
   e->total_slots = (long long)e->slots_per_stream * Bm;
   e->kpool.alloc((size_t)e->Ld * e->total_slots * d * 2);
@@ -504,7 +556,7 @@ int b200w_engine_finalize(b200w_engine* e) {
   e->scratch_i.alloc(((size_t)e->logit_rows + 4 * Bm + n) * 4);
   e->cross_off.alloc(Bm * 8);
   e->const_len.alloc(n * 4);
-  e->mask.alloc(e->V);
+  e->mask.alloc(e->V + 16);
   e->topk_ids.alloc(rows * MAX_TOPK * 4);
   e->topk_lp.alloc(rows * MAX_TOPK * 4);
   e->probs.alloc(std::max<int64_t>(n, Bm * 128) * 4);
@@ -655,6 +707,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
   }
 
   const bool timing = getenv("B200W_DECODE_TIMING") != nullptr;
+  g_optimer.on = getenv("B200W_DECODE_PROFILE") != nullptr && !e->use_graphs;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration<double, std::milli>(now() - t0).count();
@@ -779,7 +832,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     logits_for_rows(e, nullptr, m.n, s);
     SampleParams sps = sp;
     sps.state = m.state;
-    sample_topk(sps, m.n, s);
+    { OP(12); sample_topk(sps, m.n, s); }
     B200W_CHECK_CUDA(cudaMemcpyAsync(h_ids, sp.out_ids, (size_t)m.n * k_top * 4, cudaMemcpyDeviceToHost, s));
     B200W_CHECK_CUDA(cudaMemcpyAsync(h_lp, sp.out_logprobs, (size_t)m.n * k_top * 4, cudaMemcpyDeviceToHost, s));
   };
@@ -900,6 +953,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     }
     t_book += ms_since(t_s2);
   }
+  g_optimer.report("decode (prefill + steps)");
   if (timing)
     fprintf(stderr, "[b200w_decode] B=%d K=%d steps=%d prefill+first=%.2f ms, per step: fill %.3f ms, launch+gpu %.3f ms, "
             "bookkeeping %.3f ms, total %.1f ms\n", B, K, n_steps, t_prefill, t_fill / std::max(n_steps, 1),

@@ -69,11 +69,77 @@ __global__ void __launch_bounds__(128) layernorm_kernel(float* __restrict__ x, c
     }
 }
 
+// Few rows (decode steps) with pending split-K partial sums: one CTA per row, one float4 per thread, so
+// the 1 + 1 + n_partial loads of a thread are all independent and in flight together.
+__global__ void __launch_bounds__(320) layernorm_reduce_kernel(float* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, bf16* __restrict__ y,
+                                                               int d, const float* __restrict__ partial, int n_partial,
+                                                               long long partial_stride,
+                                                               const float* __restrict__ pbias) {
+  __shared__ float s_red[2][10];
+  const int row = blockIdx.x, t = threadIdx.x;
+  float4* xp = reinterpret_cast<float4*>(x + (long long)row * d);
+  float4 v = xp[t];
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(pbias) + t);
+  float4 acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* pp = reinterpret_cast<const float4*>(partial + (long long)row * d) + t;
+  const long long st4 = partial_stride / 4;
+  int sidx = 0;
+  for (; sidx + 4 <= n_partial; sidx += 4) {  // slabs are summed in a fixed order -> deterministic
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = pp[(sidx + u) * st4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc[u].x += q[u].x; acc[u].y += q[u].y; acc[u].z += q[u].z; acc[u].w += q[u].w; }
+  }
+  for (; sidx < n_partial; ++sidx) {
+    const float4 q = pp[sidx * st4];
+    acc[0].x += q.x; acc[0].y += q.y; acc[0].z += q.z; acc[0].w += q.w;
+  }
+  v.x += bb.x + ((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x));
+  v.y += bb.y + ((acc[0].y + acc[1].y) + (acc[2].y + acc[3].y));
+  v.z += bb.z + ((acc[0].z + acc[1].z) + (acc[2].z + acc[3].z));
+  v.w += bb.w + ((acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+  xp[t] = v;
+  const int warp = t >> 5, lane = t & 31, nw = blockDim.x >> 5;
+  float sum = v.x + v.y + v.z + v.w;
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_red[0][warp] = sum;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < nw; ++w) tot += s_red[0][w];
+  const float mean = tot / (float)d;
+  const float a = v.x - mean, b = v.y - mean, c = v.z - mean, e = v.w - mean;
+  float sq = a * a + b * b + c * c + e * e;
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (lane == 0) s_red[1][warp] = sq;
+  __syncthreads();
+  float tsq = 0.f;
+  for (int w = 0; w < nw; ++w) tsq += s_red[1][w];
+  const float rstd = rsqrtf(tsq / (float)d + 1e-5f);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + t), be = __ldg(reinterpret_cast<const float4*>(beta) + t);
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a * rstd * g.x + be.x, b * rstd * g.y + be.y);
+  __nv_bfloat162 hi = __floats2bfloat162_rn(c * rstd * g.z + be.z, e * rstd * g.w + be.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  reinterpret_cast<uint2*>(y + (long long)row * d)[t] = u;
+}
+
 void layernorm(float* x, const int* row_idx, const float* gamma, const float* beta, bf16* y, int rows, int d,
                cudaStream_t stream, const SplitReduce* sr) {
   if (rows <= 0) return;
   B200W_REQUIRE(d % 128 == 0 && d <= 1280, "LayerNorm width must be a multiple of 128, <= 1280");
   const bool red = sr && sr->n > 0;
+  if (red && !row_idx) {
+    layernorm_reduce_kernel<<<rows, d / 4, 0, stream>>>(x, gamma, beta, y, d, sr->partial, sr->n, sr->stride,
+                                                       sr->bias);
+    B200W_COUNT_LAUNCH();
+    B200W_CHECK_CUDA(cudaGetLastError());
+    return;
+  }
   layernorm_kernel<<<cdiv(rows, 4), 128, 0, stream>>>(x, row_idx, gamma, beta, y, rows, d,
                                                        red ? sr->partial : nullptr, red ? sr->n : 0,
                                                        red ? sr->stride : 0, red ? sr->bias : nullptr);
@@ -147,11 +213,10 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* s) {
   return r;
 }
 
-__device__ __forceinline__ bool token_masked(int v, const SampleParams& p, const int4 st,
-                                             const unsigned char* mask) {
+__device__ __forceinline__ bool token_masked_m(int v, unsigned mbyte, const SampleParams& p, const int4 st) {
   // st.x flags, st.y ts_lo
-  if (mask[v] & 1) return true;                            // static suppress list
-  if ((st.x & SF_FIRST) && (mask[v] & 2)) return true;     // suppress_blank at the first position
+  if (mbyte & 1) return true;                            // static suppress list
+  if ((st.x & SF_FIRST) && (mbyte & 2)) return true;     // suppress_blank at the first position
   if (!(st.x & SF_RULES)) return false;
   if (v == p.no_timestamps) return true;
   if (v >= p.timestamp_begin) {
@@ -163,6 +228,10 @@ __device__ __forceinline__ bool token_masked(int v, const SampleParams& p, const
     if ((st.x & SF_SUP_TEXT) && v < p.eot) return true;    // after a lone timestamp: ts or EOT
   }
   return false;
+}
+__device__ __forceinline__ bool token_masked(int v, const SampleParams& p, const int4 st,
+                                             const unsigned char* mask) {
+  return token_masked_m(v, mask[v], p, st);
 }
 
 // One CTA (1024 threads) per row: masked log-softmax with Whisper's timestamp rules, then top-k.
@@ -198,23 +267,51 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
   const int4 st = p.state[row];
   const int V = p.n_vocab;
 
+  // rows are 16-byte aligned (ld % 8 == 0): stream them as float4, the ragged tail as scalars
+  const int nv4 = V >> 2;
+  float4* lg4 = reinterpret_cast<float4*>(lg);
+  const uchar4* mk4 = reinterpret_cast<const uchar4*>(p.mask);
+  const int tb = p.timestamp_begin;
   float mx = -INFINITY, mx_text = -INFINITY;
-  for (int v = tid; v < V; v += SAMPLE_THREADS) {
-    float x = lg[v];
-    if (token_masked(v, p, st, p.mask)) {
-      x = -INFINITY;
-      lg[v] = x;
+  for (int i = tid; i < nv4; i += SAMPLE_THREADS) {
+    float4 x = lg4[i];
+    const uchar4 m = mk4[i];
+    const int v = 4 * i;
+    const bool k0 = token_masked_m(v, m.x, p, st), k1 = token_masked_m(v + 1, m.y, p, st),
+               k2 = token_masked_m(v + 2, m.z, p, st), k3 = token_masked_m(v + 3, m.w, p, st);
+    if (k0 | k1 | k2 | k3) {
+      if (k0) x.x = -INFINITY;
+      if (k1) x.y = -INFINITY;
+      if (k2) x.z = -INFINITY;
+      if (k3) x.w = -INFINITY;
+      lg4[i] = x;
     }
+    mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+    if (v < tb) mx_text = fmaxf(mx_text, x.x);
+    if (v + 1 < tb) mx_text = fmaxf(mx_text, x.y);
+    if (v + 2 < tb) mx_text = fmaxf(mx_text, x.z);
+    if (v + 3 < tb) mx_text = fmaxf(mx_text, x.w);
+  }
+  for (int v = 4 * nv4 + tid; v < V; v += SAMPLE_THREADS) {
+    float x = lg[v];
+    if (token_masked(v, p, st, p.mask)) { x = -INFINITY; lg[v] = x; }
     mx = fmaxf(mx, x);
-    if (v < p.timestamp_begin) mx_text = fmaxf(mx_text, x);
+    if (v < tb) mx_text = fmaxf(mx_text, x);
   }
   mx = block_max_1024(mx, s_red);
   mx_text = block_max_1024(mx_text, s_red);
   float sum_all = 0.f, sum_ts = 0.f;
-  for (int v = tid; v < V; v += SAMPLE_THREADS) {
-    const float e = __expf(lg[v] - mx);  // exp(-inf) = 0 for barred tokens
+  for (int i = tid; i < nv4; i += SAMPLE_THREADS) {
+    const float4 x = lg4[i];
+    const int v = 4 * i;
+    const float e0 = __expf(x.x - mx), e1 = __expf(x.y - mx), e2 = __expf(x.z - mx), e3 = __expf(x.w - mx);
+    sum_all += (e0 + e1) + (e2 + e3);
+    if (v + 3 >= tb) sum_ts += (v >= tb ? e0 : 0.f) + (v + 1 >= tb ? e1 : 0.f) + (v + 2 >= tb ? e2 : 0.f) + e3;
+  }
+  for (int v = 4 * nv4 + tid; v < V; v += SAMPLE_THREADS) {
+    const float e = __expf(lg[v] - mx);
     sum_all += e;
-    if (v >= p.timestamp_begin) sum_ts += e;
+    if (v >= tb) sum_ts += e;
   }
   sum_all = block_sum_1024(sum_all, s_red);
   sum_ts = block_sum_1024(sum_ts, s_red);
@@ -225,7 +322,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
     const float ts_logprob = mx + logf(sum_ts) - lse;
     const float text_logprob = mx_text - lse;
     if (ts_logprob > text_logprob) {
-      v_lo = p.timestamp_begin;
+      v_lo = tb;
       lse = mx + logf(sum_ts);
     }
   }
@@ -236,15 +333,25 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
 #pragma unroll
   for (int j = 0; j < MAX_TOPK; ++j) { bv[j] = -INFINITY; bi[j] = 0x7fffffff; }
   const int k = p.k;
-  for (int v = v_lo + tid; v < V; v += SAMPLE_THREADS) {
-    const float x = lg[v] - lse;
-    if (x > bv[k - 1]) {
+  float thresh = -INFINITY;  // == bv[k-1], kept in a register
+  auto consider = [&](float xr, int v) {
+    const float x = xr - lse;
+    if (v >= v_lo && x > thresh) {
       int j = k - 1;
       while (j > 0 && x > bv[j - 1]) { bv[j] = bv[j - 1]; bi[j] = bi[j - 1]; --j; }
       bv[j] = x;
       bi[j] = v;
+      thresh = bv[k - 1];
+    }
+  };
+  for (int i = tid; i < nv4; i += SAMPLE_THREADS) {
+    const float4 x = lg4[i];
+    const int v = 4 * i;
+    if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) - lse > thresh) {
+      consider(x.x, v); consider(x.y, v + 1); consider(x.z, v + 2); consider(x.w, v + 3);
     }
   }
+  for (int v = 4 * nv4 + tid; v < V; v += SAMPLE_THREADS) consider(lg[v], v);
   int head = 0;
   for (int r = 0; r < k; ++r) {
     // block argmax over every thread's current head; ties -> lower id

@@ -340,7 +340,7 @@ class B200WhisperModel:
                          max_initial_timestamp: float = 1.0, word_timestamps: bool = False,
                          prepend_punctuations: str = "\"'“¿([{-", append_punctuations: str = "\"'.。,，!！?？:：”)]}、",
                          vad_filter: bool = False, max_new_tokens: Optional[int] = None,
-                         device_audio=None, **unsupported):
+                         device_audio=None, max_rounds: Optional[int] = None, **unsupported):
         """Transcribe independent clips concurrently; returns [(segments, info)] per clip.
 
         ``device_audio=(audio_dev, offsets)`` skips the host->device copy: the clips are already
@@ -401,7 +401,7 @@ class B200WhisperModel:
                     else:
                         st.all_tokens.extend(ip)
                 streams.append(st)
-            self._run_streams(mel, streams)
+            self._run_streams(mel, streams, max_rounds)
         out = []
         for i, st in enumerate(streams):
             info = TranscriptionInfo(lang_info[i][0], float(lang_info[i][1]), durations[i], durations[i],
@@ -443,12 +443,15 @@ class B200WhisperModel:
             suppress_ids=tk.suppressed_tokens(o.suppress_tokens) if o.suppress_tokens is not None else [],
             blank_ids=tk.blank_tokens())
 
-    def _run_streams(self, mel: frontend.MelBatch, streams: List[_Stream]) -> None:
-        """Rounds of (pack windows -> encode -> cross K/V -> decode -> align) over the live streams."""
+    def _run_streams(self, mel: frontend.MelBatch, streams: List[_Stream], max_rounds: Optional[int] = None) -> None:
+        """Rounds of (pack windows -> encode -> cross K/V -> decode -> align) over the live streams.
+        ``max_rounds`` (profiling aid) stops early."""
+        rounds = 0
         while True:
             live = [s for s in streams if s.seek < s.content_frames]
-            if not live:
+            if not live or (max_rounds is not None and rounds >= max_rounds):
                 return
+            rounds += 1
             for c0 in range(0, len(live), self.max_batch):
                 self._round(mel, live[c0:c0 + self.max_batch])
 

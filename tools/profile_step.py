@@ -23,7 +23,7 @@ model = B200WhisperModel(a.model, max_batch=a.streams, max_beam=a.beam)
 audios = [speech_like(1234 + i, a.seconds) for i in range(a.streams)]
 audio_dev, offsets = FE.upload_audio(audios, dev)
 kw = dict(languages=["en"] * a.streams, beam_size=a.beam, temperature=0.0, word_timestamps=True,
-          max_new_tokens=a.max_new or None)
+          max_new_tokens=a.max_new or None, max_rounds=1)
 model.transcribe_batch(None, device_audio=(audio_dev, offsets), **kw)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
