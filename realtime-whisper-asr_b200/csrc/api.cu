@@ -17,6 +17,11 @@ static thread_local std::string t_last_error;
 void set_last_error(const std::string& s) { t_last_error = s; }
 const char* get_last_error() { return t_last_error.c_str(); }
 
+bool pdl_enabled() {
+  static const bool on = getenv("B200W_NO_PDL") == nullptr;
+  return on;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

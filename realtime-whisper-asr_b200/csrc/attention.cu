@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnPara
   const int g = blockIdx.x, h = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = p.g_start[g], nq = p.g_count[g];
+  if (nq == 0) return;
   const long long base = p.kv_base_off[p.stream[q0]];
   const bf16* kb = p.kbase + base + h * p.head_stride;
   const bf16* vb = p.vbase + base + h * p.head_stride;
@@ -645,6 +646,7 @@ __global__ void __launch_bounds__(SW * 32) cross_attn_split_kernel(const CrossAt
   const int g = blockIdx.x, h = blockIdx.y, sp = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = p.g_start[g], nq = p.g_count[g];
+  if (nq == 0) return;  // padding rows of a finished stream: nothing to attend, no K/V traffic
   const long long base = p.kv_base_off[p.stream[q0]];
   const int k_lo = sp * keys_per;
   const int n_keys = max(0, min(p.len - k_lo, keys_per));

@@ -59,6 +59,35 @@ int num_sms();
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL).  Kernels of the decode step are launched with the
+// programmatic-stream-serialization attribute: a kernel's CTAs may become resident (and run their
+// prologue: barrier init, TMEM allocation, weight prefetch) while the kernel before it is still
+// running.  Contract for every kernel launched through launch_pdl(): pdl_trigger() first, then
+// pdl_wait() in every thread BEFORE the first access to anything another kernel wrote or reads --
+// before any early return, so that grid completion always implies the predecessor's completion.
+// Both are no-ops when the kernel is launched without the attribute (B200W_NO_PDL=1).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  B200W_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+#endif
+
 // launch counter (bench.py reports gpu_launches from this)
 extern unsigned long long g_launch_count;
 #define B200W_COUNT_LAUNCH() (++::b200w::g_launch_count)

@@ -293,15 +293,18 @@ struct PassMeta {  // device pointers into e->meta for one forward pass of n tok
 // host-side staging of the metadata: [tok|pos|slot|trow|kvlen|stream] x n ints, then state int4 x n
 struct HostMeta {
   std::vector<int> tok, pos, slot, trow, kvlen, stream, parent;
+  std::vector<char> idle;  // fixed-shape decode steps: rows that only pad the batch (no cross attention)
   std::vector<int4> state;
   void clear() {
     tok.clear(); pos.clear(); slot.clear(); trow.clear(); kvlen.clear(); stream.clear(); parent.clear();
+    idle.clear();
     state.clear();
   }
   int n() const { return (int)tok.size(); }
-  void push(int t, int p, int s, int tr, int kl, int st, int4 sstate = make_int4(0, 0, 0, 0), int par = 0) {
+  void push(int t, int p, int s, int tr, int kl, int st, int4 sstate = make_int4(0, 0, 0, 0), int par = 0,
+            bool is_idle = false) {
     tok.push_back(t); pos.push_back(p); slot.push_back(s); trow.push_back(tr); kvlen.push_back(kl);
-    stream.push_back(st); parent.push_back(par); state.push_back(sstate);
+    stream.push_back(st); parent.push_back(par); state.push_back(sstate); idle.push_back(is_idle ? 1 : 0);
   }
 };
 
@@ -316,8 +319,13 @@ PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) 
   for (int i = 0; i < n;) {
     int j = i + 1;
     while (j < n && j - i < CROSS_GROUP && h.stream[j] == h.stream[i]) ++j;
+    // idle rows sit behind the live rows of their stream: the group covers the same rows every step
+    // (fixed shape) but only its leading live rows are attended, and a fully idle group reads no K/V
+    int live = 0;
+    while (i + live < j && !h.idle[i + live]) ++live;
+    for (int r = i + live; r < j; ++r) B200W_REQUIRE(h.idle[r], "live decoder row behind an idle one");
     gs.push_back(i);
-    gc.push_back(j - i);
+    gc.push_back(live);
     i = j;
   }
   const int ng = (int)gs.size();
@@ -346,7 +354,8 @@ PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) 
   m.g_count = dp + 7 * n + ng;
   m.n_groups = ng;
   m.max_group = 1;
-  for (int c : gc) m.max_group = std::max(m.max_group, c);
+  for (size_t g = 0; g < gs.size(); ++g)  // capacity, not the live count: keeps the launch shape fixed
+    m.max_group = std::max(m.max_group, (g + 1 < gs.size() ? gs[g + 1] : n) - gs[g]);
   m.state = reinterpret_cast<int4*>(reinterpret_cast<char*>(dp) + st_off);
   return m;
 }
@@ -538,6 +547,7 @@ int b200w_engine_finalize(b200w_engine* e) {
   e->d_h.alloc(n * d * 2);
   e->d_qkv.alloc(n * 3 * d * 2);
   e->d_attn.alloc(n * d * 2);
+  B200W_CHECK_CUDA(cudaMemset(e->d_attn.p, 0, n * d * 2));  // padding rows are never written: keep them finite
   e->d_cq.alloc(n * d * 2);
   e->d_mlp.alloc(n * 4 * d * 2);
   e->d_split.alloc((size_t)(128 * 160 * 64) * 16 * 4);
@@ -854,7 +864,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
           any = true;
         } else {  // idle row: one dummy token at position 0 in a scratch slot of its own
           hm.push(o.eot, 0, b * e->slots_per_stream + e->slots_per_stream - 1 - k, row, 1, b,
-                  make_int4(0, 0, 0, 0), row);
+                  make_int4(0, 0, 0, 0), row, true);
         }
       }
     }

@@ -1,7 +1,9 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:
 //   TMA (128B-swizzled tiles) -> shared memory ring -> tcgen05.mma (fp32 accumulators in TMEM,
 //   double-buffered) -> tcgen05.ld epilogue (bias / GELU / residual / bf16|fp32 store).
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue (two warps per
+// TMEM lane quarter, each draining half of the tile's columns: the GELU / bias / convert work of a
+// 128x256 tile must finish inside the ~10k cycles the tensor pipe needs for the next one).
 // The A operand may be addressed through up to three "taps" (row shift + column offset), which
 // turns the same kernel into an implicit-GEMM conv1d over time-major activations; TMA zero-fills
 // the out-of-range rows that the conv padding needs.
@@ -16,6 +18,8 @@ namespace b200w {
 
 static constexpr int BM = 128, BK = 64;
 static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+static constexpr int EPI_WARPS = 8;
+static constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
 
 struct GemmParams {
   int out_rows, batches, N;
@@ -121,7 +125,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 // 32 streams): both 128-row tiles are computed from ONE pass over the weight tile, which halves the
 // weight traffic and the number of CTAs' worth of fixed cost.
 template <int BN, int STAGES, int MP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
   constexpr int B_BYTES = BN * BK * 2;
@@ -150,7 +154,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 128);
+      mbar_init(tempty0 + 8 * a, EPI_WARPS * 32);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -223,8 +227,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {  // ---------------- epilogue warps 2..5 (TMEM lane quarter = warp % 4)
+  } else {  // ---------------- epilogue warps 2..9 (TMEM lane quarter = warp % 4, column half = (warp-2)/4)
     const int q = warp & 3;
+    constexpr int CW = BN / 2;  // columns per warp
+    const int cbeg = ((warp - 2) >> 2) * CW;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
@@ -239,11 +245,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool row_ok = r < p.out_rows;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + mi * BN;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = cbeg; c0 < cbeg + CW; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
-          if (mi == MP - 1 && c0 + 32 == BN) {  // accumulator drained: hand the TMEM stage back
+          if (mi == MP - 1 && c0 + 32 == cbeg + CW) {  // this warp's share is drained: hand the TMEM stage back
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * acc);
           }
@@ -365,7 +371,7 @@ static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmPara
     ps = prof_slot(2.0 * (double)p.out_rows * p.batches * (double)p.N * (double)p.total_kb * BK);
     B200W_CHECK_CUDA(cudaEventRecord(ps->beg, stream));
   }
-  gemm_tcgen05_kernel<BN, STAGES, MP><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BN, STAGES, MP><<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
   if (ps) B200W_CHECK_CUDA(cudaEventRecord(ps->end, stream));
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());

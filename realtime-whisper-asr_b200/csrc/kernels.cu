@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(128) layernorm_kernel(float* __restrict__ x, c
                                                         int rows, int d, const float* __restrict__ partial,
                                                         int n_partial, long long partial_stride,
                                                         const float* __restrict__ pbias) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -77,10 +79,13 @@ __global__ void __launch_bounds__(320) layernorm_reduce_kernel(float* __restrict
                                                                long long partial_stride,
                                                                const float* __restrict__ pbias) {
   __shared__ float s_red[2][10];
+  pdl_trigger();
   const int row = blockIdx.x, t = threadIdx.x;
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(pbias) + t);  // weights: safe ahead of the wait
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + t), be = __ldg(reinterpret_cast<const float4*>(beta) + t);
+  pdl_wait();
   float4* xp = reinterpret_cast<float4*>(x + (long long)row * d);
   float4 v = xp[t];
-  const float4 bb = __ldg(reinterpret_cast<const float4*>(pbias) + t);
   float4 acc[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -119,7 +124,6 @@ __global__ void __launch_bounds__(320) layernorm_reduce_kernel(float* __restrict
   float tsq = 0.f;
   for (int w = 0; w < nw; ++w) tsq += s_red[1][w];
   const float rstd = rsqrtf(tsq / (float)d + 1e-5f);
-  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + t), be = __ldg(reinterpret_cast<const float4*>(beta) + t);
   __nv_bfloat162 lo = __floats2bfloat162_rn(a * rstd * g.x + be.x, b * rstd * g.y + be.y);
   __nv_bfloat162 hi = __floats2bfloat162_rn(c * rstd * g.z + be.z, e * rstd * g.w + be.w);
   uint2 u;
@@ -134,15 +138,15 @@ void layernorm(float* x, const int* row_idx, const float* gamma, const float* be
   B200W_REQUIRE(d % 128 == 0 && d <= 1280, "LayerNorm width must be a multiple of 128, <= 1280");
   const bool red = sr && sr->n > 0;
   if (red && !row_idx) {
-    layernorm_reduce_kernel<<<rows, d / 4, 0, stream>>>(x, gamma, beta, y, d, sr->partial, sr->n, sr->stride,
-                                                       sr->bias);
+    launch_pdl(layernorm_reduce_kernel, dim3(rows), dim3(d / 4), 0, stream, x, gamma, beta, y, d, sr->partial, sr->n,
+               sr->stride, sr->bias);
     B200W_COUNT_LAUNCH();
     B200W_CHECK_CUDA(cudaGetLastError());
     return;
   }
-  layernorm_kernel<<<cdiv(rows, 4), 128, 0, stream>>>(x, row_idx, gamma, beta, y, rows, d,
-                                                       red ? sr->partial : nullptr, red ? sr->n : 0,
-                                                       red ? sr->stride : 0, red ? sr->bias : nullptr);
+  launch_pdl(layernorm_kernel, dim3(cdiv(rows, 4)), dim3(128), 0, stream, x, row_idx, gamma, beta, y, rows, d,
+             red ? sr->partial : (const float*)nullptr, red ? sr->n : 0, red ? sr->stride : 0LL,
+             red ? sr->bias : (const float*)nullptr);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }
@@ -151,6 +155,8 @@ void layernorm(float* x, const int* row_idx, const float* gamma, const float* be
 __global__ void embed_kernel(const int* __restrict__ tok, const int* __restrict__ pos,
                              const bf16* __restrict__ tok_emb, const float* __restrict__ pos_emb,
                              float* __restrict__ x, int d) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.x;
   const bf16* te = tok_emb + (long long)tok[n] * d;
   const float* pe = pos_emb + (long long)pos[n] * d;
@@ -164,7 +170,7 @@ __global__ void embed_kernel(const int* __restrict__ tok, const int* __restrict_
 void embed_tokens(const int* tok, const int* pos, const bf16* tok_emb, const float* pos_emb, float* x,
                   int n, int d, cudaStream_t stream) {
   if (n <= 0) return;
-  embed_kernel<<<n, 128, 0, stream>>>(tok, pos, tok_emb, pos_emb, x, d);
+  launch_pdl(embed_kernel, dim3(n), dim3(128), 0, stream, tok, pos, tok_emb, pos_emb, x, d);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }
@@ -173,6 +179,8 @@ void embed_tokens(const int* tok, const int* pos, const bf16* tok_emb, const flo
 // qkv bf16 [n][3d] -> kpool[slot[n]][d], vpool[slot[n]][d]
 __global__ void kv_scatter_kernel(const bf16* __restrict__ qkv, const int* __restrict__ slot,
                                   bf16* __restrict__ kpool, bf16* __restrict__ vpool, int d) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.x;
   const long long s = slot[n];
   const uint4* src = reinterpret_cast<const uint4*>(qkv + (long long)n * 3 * d + d);
@@ -188,7 +196,7 @@ __global__ void kv_scatter_kernel(const bf16* __restrict__ qkv, const int* __res
 void kv_scatter(const bf16* qkv, const int* slot, bf16* kpool, bf16* vpool, int n, int d,
                 cudaStream_t stream) {
   if (n <= 0) return;
-  kv_scatter_kernel<<<n, 128, 0, stream>>>(qkv, slot, kpool, vpool, d);
+  launch_pdl(kv_scatter_kernel, dim3(n), dim3(128), 0, stream, qkv, slot, kpool, vpool, d);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }
