@@ -38,6 +38,9 @@ uint64_t b200w_launch_count(void);
 /* Measurement hook: record CUDA events around every GEMM launch of one tile-width class
  * (bn = 64 | 128 | 256) until _end, which synchronises those events and returns the summed device
  * time (ms), the summed algorithmic flops (2*M*N*K per launch) and the launch count. */
+/* Development aid: every CTA of later GEMM launches writes 16 int64 timestamps (clock64 / globaltimer)
+ * to dev_buf; NULL switches it off. */
+int b200w_gemm_set_trace(void* dev_buf);
 int b200w_gemm_profile_begin(int bn);
 int b200w_gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches);
 
@@ -75,7 +78,8 @@ int b200w_dedup_features(const float* audio_dev, const int64_t* offsets_dev, int
 /* ---------------------------------------------------------------- building blocks (tests) ---- */
 
 /* out[M][N] = act(A[M][K] * W[N][K]^T + bias) + residual.  bf16 operands, fp32 accumulate on
- * tcgen05.  flags: bit0 out fp32, bit1 residual fp32, bit2 GELU.  force_bn: 0 | 64 | 128 | 256. */
+ * tcgen05.  flags: bit0 out fp32, bit1 residual fp32, bit2 GELU, bits 8..15 split-K count s (> 1: out
+ * receives fp32 partial sums [s][M][ldo], no bias / activation / residual).  force_bn: 0 | 64 | 128 | 256. */
 int b200w_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev,
                     const void* residual_dev, void* out_dev, int M, int N, int K, int64_t lda,
                     int64_t ldw, int64_t ldr, int64_t ldo, int flags, int force_bn, void* stream);

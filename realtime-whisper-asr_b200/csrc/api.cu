@@ -42,6 +42,11 @@ const char* b200w_last_error(void) { return get_last_error(); }
 int b200w_abi_version(void) { return B200W_ABI_VERSION; }
 uint64_t b200w_launch_count(void) { return g_launch_count; }
 
+int b200w_gemm_set_trace(void* dev_buf) {
+  gemm_set_trace(dev_buf);
+  return 0;
+}
+
 int b200w_gemm_profile_begin(int bn) {
   B200W_API_BEGIN
   gemm_profile_begin(bn);
@@ -111,6 +116,10 @@ int b200w_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev,
   d.out_fp32 = (flags & 1) ? 1 : 0;
   d.out_row_stride = ldo;
   d.force_bn = force_bn;
+  if ((flags >> 8) & 0xff) {  // split-K: out = fp32 partial sums [splits][M][ldo]
+    d.split_k = (flags >> 8) & 0xff;
+    d.split_stride = (int64_t)M * ldo;
+  }
   gemm_bf16(d, static_cast<cudaStream_t>(stream));
   B200W_API_END
 }

@@ -233,6 +233,8 @@ static constexpr int DEC_WARPS = 2;
 
 __global__ void __launch_bounds__(DEC_WARPS * 32) dec_attn_kernel(const DecAttnParams p) {
   extern __shared__ float s_scores[];  // [DEC_WARPS][max_len]
+  pdl_trigger();
+  pdl_wait();
   const int qi = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y * DEC_WARPS + warp;
@@ -328,7 +330,7 @@ void dec_attention(const DecAttnParams& p, int n_heads, cudaStream_t stream) {
   if (p.n_queries <= 0) return;
   B200W_REQUIRE(n_heads % DEC_WARPS == 0, "head count must be even");
   const size_t smem = (size_t)DEC_WARPS * p.max_len * sizeof(float);
-  dec_attn_kernel<<<dim3(p.n_queries, n_heads / DEC_WARPS), DEC_WARPS * 32, smem, stream>>>(p);
+  launch_pdl(dec_attn_kernel, dim3(p.n_queries, n_heads / DEC_WARPS), dim3(DEC_WARPS * 32), smem, stream, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }
@@ -352,6 +354,8 @@ __global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnPara
   float* s_acc = s_sc + XQ * len_pad;       // [XW][XQ][64]
   const int g = blockIdx.x, h = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
+  pdl_wait();
   const int q0 = p.g_start[g], nq = p.g_count[g];
   if (nq == 0) return;
   const long long base = p.kv_base_off[p.stream[q0]];
@@ -645,6 +649,8 @@ __global__ void __launch_bounds__(SW * 32) cross_attn_split_kernel(const CrossAt
   float* s_ml = s_acc + SW * XQ * HD;        // [2][8]
   const int g = blockIdx.x, h = blockIdx.y, sp = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
+  pdl_wait();
   const int q0 = p.g_start[g], nq = p.g_count[g];
   if (nq == 0) return;  // padding rows of a finished stream: nothing to attend, no K/V traffic
   const long long base = p.kv_base_off[p.stream[q0]];
@@ -762,6 +768,8 @@ __global__ void __launch_bounds__(SW * 32) cross_attn_split_kernel(const CrossAt
 __global__ void cross_attn_merge_kernel(const CrossAttnParams p, const float* __restrict__ part) {
   const int g = blockIdx.x, h = blockIdx.y;
   const int q = threadIdx.x >> 6, c = threadIdx.x & 63;
+  pdl_trigger();
+  pdl_wait();
   if (q >= p.g_count[g]) return;
   const float* rec = part + (((long long)g * gridDim.y + h) * KSPLIT) * (8 * 66) + q * 66;
   float M = -INFINITY;
@@ -782,9 +790,273 @@ template <int XQ>
 static void launch_cross_split(const CrossAttnParams& p, int n_groups, int n_heads, float* part, cudaStream_t stream) {
   const int keys_per = ((p.len + KSPLIT - 1) / KSPLIT + 31) & ~31;
   const size_t smem = sizeof(float) * (XQ * HD + (size_t)XQ * keys_per + (size_t)SW * XQ * HD + 16);
-  cross_attn_split_kernel<XQ><<<dim3(n_groups, n_heads, KSPLIT), SW * 32, smem, stream>>>(p, part);
+  launch_pdl(cross_attn_split_kernel<XQ>, dim3(n_groups, n_heads, KSPLIT), dim3(SW * 32), smem, stream, p, part);
   B200W_COUNT_LAUNCH();
-  cross_attn_merge_kernel<<<dim3(n_groups, n_heads), XQ * 64, 0, stream>>>(p, part);
+  launch_pdl(cross_attn_merge_kernel, dim3(n_groups, n_heads), dim3(XQ * 64), 0, stream, p, (const float*)part);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+// ---- tensor-core variant for decode steps (no probability export).
+// One persistent CTA per SM walks the (live group, head) work items.  Per item the head's K and V
+// ([1500][64] bf16 each, 384 KB together) stream ONCE through a 12-slot TMA ring, prefetched across
+// phases and across items, and the arithmetic runs on tcgen05:
+//   S^T[keys x 16] = K_tile[128 keys x 64] . Q^T        (12 tiles -> 192 TMEM columns, keys = lanes)
+//   softmax over keys: every thread owns one key row of each tile (96 scores in registers)
+//   O[128 x 64]   += P[128 x 128 keys] . V_tile[128 keys x 64]   (rows >= 8 of P are don't-care: a
+//   row of A only feeds the same row of D, so the operand tile may overlap unrelated shared memory)
+// Warps 0-3: Q staging, softmax, output.  Warp 4: TMA producer.  Warp 5: MMA issuer.
+static constexpr int XT_RING = 12;
+static constexpr int XT_MAX_TILES = 12;  // keys <= 1536
+static constexpr int XT_P_BYTES = XT_MAX_TILES * 2 * 1024;
+static constexpr int XT_Q_BYTES = 2048;
+static constexpr int XT_SMEM = XT_P_BYTES + XT_Q_BYTES + XT_RING * TILE_BYTES + 512 + 1024;
+
+struct CrossTcParams {
+  const bf16* q;
+  int q_stride;
+  const int* stream;
+  const int* g_start;
+  const int* g_count;
+  const int* n_live_groups;  // device: groups [0, n_live) have at least one live row
+  int n_heads;
+  int blocks_per_stream;  // L * 2 * H  ([1500][64] blocks per stream in the cross K/V buffer)
+  int layer_block0;       // 2 * layer * H
+  int len;
+  bf16* out;
+  int out_stride;
+  float scale_log2e;
+};
+
+__global__ void __launch_bounds__(192, 1)
+cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sP = smem;
+  uint8_t* sQ = sP + XT_P_BYTES;
+  uint8_t* ring = sQ + XT_Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + XT_RING * TILE_BYTES);
+  float* s_red = reinterpret_cast<float*>(bars + 2 * XT_RING + 4);  // [2][4][8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_red + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + XT_RING);
+  const uint32_t bar_q = smem_u32(bars + 2 * XT_RING), bar_s = bar_q + 8, bar_p = bar_q + 16, bar_o = bar_q + 24;
+  pdl_trigger();
+  if (tid == 0) {
+    for (int i = 0; i < XT_RING; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    mbar_init(bar_q, 128);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmKV);
+  }
+  if (warp == 5) {
+    tmem_alloc(smem_u32(tmem_slot), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_S = *tmem_slot, tmem_O = tmem_S + 16 * XT_MAX_TILES;
+  const int n_tiles = (p.len + 127) >> 7;
+  // K/V and the pass metadata were written long before the kernel ahead of this one started, so the
+  // producer may run ahead of the dependency wait; Q (read) and the output (written) may not.
+  const int n_items = *p.n_live_groups * p.n_heads;
+
+  if (warp == 4) {
+    if (lane == 0) {  // ---------------- TMA producer: K tiles then V tiles of every item
+      uint32_t slot = 0, phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int g = item / p.n_heads, h = item - g * p.n_heads;
+        const int blk = p.stream[p.g_start[g]] * p.blocks_per_stream + p.layer_block0 + h;
+        for (int kv = 0; kv < 2; ++kv)
+          for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(empty0 + 8 * slot, phase ^ 1);
+            const uint32_t fb = full0 + 8 * slot;
+            mbar_arrive_expect_tx(fb, TILE_BYTES);
+            tma_load_3d(smem_u32(ring + slot * TILE_BYTES), &tmKV, fb, 0, j * 128, blk + kv * p.n_heads);
+            if (++slot == XT_RING) { slot = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      constexpr uint32_t idescS = make_idesc_bf16(128, 16, 0, 0);  // K (K-major) x Q (K-major)
+      constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);  // P (K-major) x V (MN-major)
+      uint32_t slot = 0, phase = 0, it = 0;
+      const uint64_t qd = make_sw128_desc(smem_u32(sQ));
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        mbar_wait(bar_q, it & 1);
+        tc_fence_after();
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(full0 + 8 * slot, phase);
+          tc_fence_after();
+          const uint64_t kd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_S + 16 * j, kd + 2 * k, qd + 2 * k, idescS, k != 0);
+          tc_commit(empty0 + 8 * slot);
+          if (++slot == XT_RING) { slot = 0; phase ^= 1; }
+        }
+        tc_commit(bar_s);
+        mbar_wait(bar_p, it & 1);
+        tc_fence_after();
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(full0 + 8 * slot, phase);
+          tc_fence_after();
+          const uint64_t vd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t pd = make_sw128_desc(smem_u32(sP + (j * 2 + (k >> 2)) * 1024)) + 2 * (k & 3);
+            tc_mma_bf16(tmem_O, pd, vd + 128 * k, idescO, (j | k) != 0);
+          }
+          tc_commit(empty0 + 8 * slot);
+          if (++slot == XT_RING) { slot = 0; phase ^= 1; }
+        }
+        tc_commit(bar_o);
+      }
+    }
+  } else {  // ---------------- warps 0..3: Q staging, softmax (thread = key row of every tile), output
+    pdl_wait();
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int g = item / p.n_heads, h = item - g * p.n_heads;
+      const int q0 = p.g_start[g], nq = p.g_count[g];
+      {  // Q -> swizzled K-major [16][64] tile (rows >= nq zero)
+        const int qr = tid >> 3, ch = tid & 7;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (qr < nq) u = *reinterpret_cast<const uint4*>(p.q + (long long)(q0 + qr) * p.q_stride + h * HD + 8 * ch);
+        *reinterpret_cast<uint4*>(sQ + qr * 128 + ((ch ^ (qr & 7)) << 4)) = u;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_q);
+      mbar_wait(bar_s, it & 1);
+      tc_fence_after();
+      // scores of this thread's key in every tile, 8 query columns each
+      uint32_t sc[XT_MAX_TILES][8];
+#pragma unroll
+      for (int j = 0; j < XT_MAX_TILES; ++j)
+        if (j < n_tiles) tmem_ld8(tmem_S + lane_sel + 16 * j, sc[j]);
+      tmem_ld_wait();
+      float mx[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mx[q] = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < XT_MAX_TILES; ++j)
+        if (j < n_tiles && j * 128 + tid < p.len) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) mx[q] = fmaxf(mx[q], __uint_as_float(sc[j][q]));
+        }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        for (int o = 16; o > 0; o >>= 1) mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
+      }
+      if (lane < 8) {
+        float v = mx[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) v = lane == q ? mx[q] : v;
+        s_red[warp * 8 + lane] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float sum[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float m = fmaxf(fmaxf(s_red[q], s_red[8 + q]), fmaxf(s_red[16 + q], s_red[24 + q]));
+        mx[q] = m * p.scale_log2e;
+        sum[q] = 0.f;
+      }
+      // P = exp2(s * c - m * c) as bf16 into the K-major operand tiles (row = query, column = key)
+      const int kc = tid & 63, half = tid >> 6;
+      uint8_t* prow = sP + half * 1024 + (kc & 7) * 2;
+#pragma unroll
+      for (int j = 0; j < XT_MAX_TILES; ++j)
+        if (j < n_tiles) {
+          const bool valid = j * 128 + tid < p.len;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float e = valid ? ex2_approx(fmaf(__uint_as_float(sc[j][q]), p.scale_log2e, -mx[q])) : 0.f;
+            sum[q] += e;
+            *reinterpret_cast<bf16*>(prow + j * 2048 + q * 128 + (((kc >> 3) ^ q) << 4)) = __float2bfloat16(e);
+          }
+        }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        for (int o = 16; o > 0; o >>= 1) sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
+      }
+      if (lane < 8) {
+        float v = sum[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) v = lane == q ? sum[q] : v;
+        s_red[32 + warp * 8 + lane] = v;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      mbar_wait(bar_o, it & 1);
+      tc_fence_after();
+      if (warp == 0) {
+        uint32_t o0[32], o1[32];
+        tmem_ld32(tmem_O, o0);
+        tmem_ld32(tmem_O + 32, o1);
+        tmem_ld_wait();
+        if (lane < nq) {
+          // the other warps' partial sums were stored before their arrive on bar_p, which bar_o follows
+          const float inv = 1.0f / (s_red[32 + lane] + s_red[40 + lane] + s_red[48 + lane] + s_red[56 + lane]);
+          bf16* dst = p.out + (long long)(q0 + lane) * p.out_stride + h * HD;
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            uint4 u, w;
+            __nv_bfloat162* u2 = reinterpret_cast<__nv_bfloat162*>(&u);
+            __nv_bfloat162* w2 = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              u2[i] = __floats2bfloat162_rn(__uint_as_float(o0[c + 2 * i]) * inv, __uint_as_float(o0[c + 2 * i + 1]) * inv);
+              w2[i] = __floats2bfloat162_rn(__uint_as_float(o1[c + 2 * i]) * inv, __uint_as_float(o1[c + 2 * i + 1]) * inv);
+            }
+            *reinterpret_cast<uint4*>(dst + c) = u;
+            *reinterpret_cast<uint4*>(dst + 32 + c) = w;
+          }
+        }
+      }
+      tc_fence_before();
+      // s_red / sQ / sP are rewritten by the next item: everyone must be past their reads first
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tmem_dealloc(tmem_S, 256);
+  }
+}
+
+void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int layer, int n_heads, int len,
+                        const bf16* q, int q_stride, const int* stream, const int* g_start, const int* g_count,
+                        const int* n_live_groups, int n_groups, bf16* out, int out_stride, float scale,
+                        cudaStream_t cs) {
+  if (n_groups <= 0) return;
+  B200W_REQUIRE(len <= 128 * XT_MAX_TILES, "cross_attention_tc: at most 1536 keys");
+  CUtensorMap tm;
+  make_tmap_bf16_3d(&tm, cross_kv, HD, len, (uint64_t)n_streams * n_layers * 2 * n_heads, HD, (uint64_t)len * HD, HD,
+                    128);
+  static bool configured = false;
+  if (!configured) {
+    B200W_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM));
+    configured = true;
+  }
+  CrossTcParams p;
+  p.q = q; p.q_stride = q_stride; p.stream = stream; p.g_start = g_start; p.g_count = g_count;
+  p.n_live_groups = n_live_groups; p.n_heads = n_heads; p.blocks_per_stream = n_layers * 2 * n_heads;
+  p.layer_block0 = 2 * layer * n_heads; p.len = len; p.out = out; p.out_stride = out_stride;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  const int items = n_groups * n_heads;
+  launch_pdl(cross_attn_tc_kernel, dim3(items < num_sms() ? items : num_sms()), dim3(192), (size_t)XT_SMEM, cs, tm, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }
@@ -802,7 +1074,7 @@ static void launch_cross_attn(const CrossAttnParams& p, int n_groups, int n_head
     B200W_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_kernel<XQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  cross_attn_kernel<XQ><<<dim3(n_groups, n_heads), XW * 32, smem, stream>>>(p);
+  launch_pdl(cross_attn_kernel<XQ>, dim3(n_groups, n_heads), dim3(XW * 32), smem, stream, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }

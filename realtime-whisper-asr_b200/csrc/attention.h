@@ -63,4 +63,12 @@ void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, int ma
 size_t cross_attention_scratch_bytes(int n_groups, int n_heads);
 static constexpr int CROSS_GROUP = 8;
 
+// Decode-step cross attention on tcgen05 (no probability export).  cross_kv is the whole per-chunk
+// buffer [n_streams][n_layers][k|v][n_heads][len][64]; groups [0, *n_live_groups) are processed, each
+// with g_count <= 8 live rows starting at g_start.
+void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int layer, int n_heads, int len,
+                        const bf16* q, int q_stride, const int* stream, const int* g_start, const int* g_count,
+                        const int* n_live_groups, int n_groups, bf16* out, int out_stride, float scale,
+                        cudaStream_t cs);
+
 }  // namespace b200w

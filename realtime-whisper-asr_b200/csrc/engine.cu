@@ -246,6 +246,13 @@ struct OpScope {
   }
 };
 #define OP(id) OpScope _op_scope_##id(id, s)
+// Development aid: B200W_ABLATE=<bit mask over the op ids above> drops those ops from the decoder pass
+// (results are garbage) so that an op's real cost inside the captured step can be read off the step time.
+static unsigned ablate_mask() {
+  static const unsigned m = getenv("B200W_ABLATE") ? (unsigned)strtoul(getenv("B200W_ABLATE"), nullptr, 0) : 0u;
+  return m;
+}
+#define RUN(id) if (!((ablate_mask() >> (id)) & 1u))
 
 // x += A W^T + b for the decoder's residual stream.  Skinny calls (decode steps) are split along K so
 // that enough CTAs stream the weights; the partial sums are handed to the next LayerNorm.
@@ -285,7 +292,8 @@ SplitReduce residual_linear(b200w_engine* e, const bf16* A, int M, int K, const 
 struct PassMeta {  // device pointers into e->meta for one forward pass of n tokens
   int n = 0;
   int *tok, *pos, *slot, *trow, *kvlen, *stream, *parent;
-  int *g_start, *g_count;  // cross-attention groups: runs of <= 8 rows of one stream
+  int *g_start, *g_count;  // cross-attention groups: runs of <= 8 rows of one stream (live groups first)
+  int* n_live = nullptr;   // device: number of groups with at least one live row
   int n_groups = 0, max_group = 1;
   int4* state;
 };
@@ -329,7 +337,20 @@ PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) 
     i = j;
   }
   const int ng = (int)gs.size();
-  const size_t ints = (size_t)n * 7 + 2 * (size_t)ng, bytes = ints * 4 + (size_t)n * 16 + 16;
+  int max_cap = 1;
+  for (int g = 0; g < ng; ++g) max_cap = std::max(max_cap, (g + 1 < ng ? gs[g + 1] : n) - gs[g]);
+  // live groups first (the order of the groups is free): the tensor-core kernel walks [0, n_live)
+  int n_live = 0;
+  {
+    std::vector<int> gs2, gc2;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int g = 0; g < ng; ++g)
+        if ((gc[g] > 0) == (pass == 0)) { gs2.push_back(gs[g]); gc2.push_back(gc[g]); }
+    for (int g = 0; g < ng; ++g) n_live += gc[g] > 0;
+    gs.swap(gs2);
+    gc.swap(gc2);
+  }
+  const size_t ints = (size_t)n * 7 + 2 * (size_t)ng + 1, bytes = ints * 4 + (size_t)n * 16 + 16;
   e->h_meta.alloc(bytes);
   int* hp = e->h_meta.as<int>();
   memcpy(hp, h.tok.data(), n * 4);
@@ -341,6 +362,7 @@ PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) 
   memcpy(hp + 6 * n, h.parent.data(), n * 4);
   memcpy(hp + 7 * n, gs.data(), ng * 4);
   memcpy(hp + 7 * n + ng, gc.data(), ng * 4);
+  hp[7 * n + 2 * ng] = n_live;
   const size_t st_off = (ints * 4 + 15) / 16 * 16;
   memcpy(reinterpret_cast<char*>(hp) + st_off, h.state.data(), (size_t)n * 16);
   *copy_bytes = st_off + (size_t)n * 16;
@@ -353,9 +375,8 @@ PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) 
   m.g_start = dp + 7 * n;
   m.g_count = dp + 7 * n + ng;
   m.n_groups = ng;
-  m.max_group = 1;
-  for (size_t g = 0; g < gs.size(); ++g)  // capacity, not the live count: keeps the launch shape fixed
-    m.max_group = std::max(m.max_group, (g + 1 < gs.size() ? gs[g + 1] : n) - gs[g]);
+  m.n_live = dp + 7 * n + 2 * ng;
+  m.max_group = max_cap;  // capacity, not the live count: keeps the launch shape fixed
   m.state = reinterpret_cast<int4*>(reinterpret_cast<char*>(dp) + st_off);
   return m;
 }
@@ -383,26 +404,26 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
   bf16* attn = e->d_attn.as<bf16>();
   bf16* cq = e->d_cq.as<bf16>();
   bf16* mlp = e->d_mlp.as<bf16>();
-  { OP(0); embed_tokens(m.tok, m.pos, e->tok_emb, e->dec_pos, x, n, d, s); }
+  RUN(0) { OP(0); embed_tokens(m.tok, m.pos, e->tok_emb, e->dec_pos, x, n, d, s); }
   SplitReduce pend;
   for (int l = 0; l < e->Ld; ++l) {
     const DecLayer& L = e->dec[l];
     bf16* kp = e->kpool.as<bf16>() + (long long)l * e->total_slots * d;
     bf16* vp = e->vpool.as<bf16>() + (long long)l * e->total_slots * d;
     // self attention
-    { OP(1); layernorm(x, nullptr, L.ln1.g, L.ln1.b, h, n, d, s, &pend); }
-    { OP(2); linear(h, n, d, L.qkv, 3 * d, qkv, 3 * d, 0, 0, nullptr, 0, 0, s); }
-    { OP(3); kv_scatter(qkv, m.slot, kp, vp, n, d, s); }
+    RUN(1) { OP(1); layernorm(x, nullptr, L.ln1.g, L.ln1.b, h, n, d, s, &pend); }
+    RUN(2) { OP(2); linear(h, n, d, L.qkv, 3 * d, qkv, 3 * d, 0, 0, nullptr, 0, 0, s); }
+    RUN(3) { OP(3); kv_scatter(qkv, m.slot, kp, vp, n, d, s); }
     DecAttnParams a;
     a.q = qkv; a.q_stride = 3 * d;
     a.kbase = kp; a.vbase = vp; a.kv_row_stride = d;
     a.table = table; a.table_stride = e->Tctx; a.trow = m.trow; a.kvlen = m.kvlen;
     a.out = attn; a.out_stride = d; a.scale = 0.125f; a.n_queries = n; a.max_len = max_kvlen;
-    { OP(4); dec_attention(a, e->H, s); }
-    { OP(5); pend = residual_linear(e, attn, n, d, L.out, x, s); }
+    RUN(4) { OP(4); dec_attention(a, e->H, s); }
+    RUN(5) { OP(5); pend = residual_linear(e, attn, n, d, L.out, x, s); }
     // cross attention
-    { OP(1); layernorm(x, nullptr, L.ln2.g, L.ln2.b, h, n, d, s, &pend); }
-    { OP(6); linear(h, n, d, L.cq, d, cq, d, 0, 0, nullptr, 0, 0, s); }
+    RUN(1) { OP(1); layernorm(x, nullptr, L.ln2.g, L.ln2.b, h, n, d, s, &pend); }
+    RUN(6) { OP(6); linear(h, n, d, L.cq, d, cq, d, 0, 0, nullptr, 0, 0, s); }
     CrossAttnParams c;
     c.q = cq; c.q_stride = d;
     // cross K/V layout [stream][layer][k|v][head][1500][64]
@@ -420,12 +441,20 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
       c.probs_out = ax->probs;
       c.probs_stride = e->Tenc;
     }
-    { OP(7); cross_attention(c, m.n_groups, e->H, m.max_group, s, e->x_split.as<float>()); }
-    { OP(8); pend = residual_linear(e, attn, n, d, L.cout, x, s); }
+    static const bool use_tc = getenv("B200W_NO_CROSS_TC") == nullptr;
+    RUN(7) {
+      OP(7);
+      if (use_tc && !c.head_export && m.max_group <= CROSS_GROUP && m.n_groups <= 64)
+        cross_attention_tc(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, d, m.stream, m.g_start, m.g_count,
+                           m.n_live, m.n_groups, attn, d, 0.125f, s);
+      else
+        cross_attention(c, m.n_groups, e->H, m.max_group, s, e->x_split.as<float>());
+    }
+    RUN(8) { OP(8); pend = residual_linear(e, attn, n, d, L.cout, x, s); }
     // MLP
-    { OP(1); layernorm(x, nullptr, L.ln3.g, L.ln3.b, h, n, d, s, &pend); }
-    { OP(9); linear(h, n, d, L.fc1, 4 * d, mlp, 4 * d, 0, 1, nullptr, 0, 0, s); }
-    { OP(10); pend = residual_linear(e, mlp, n, 4 * d, L.fc2, x, s); }
+    RUN(1) { OP(1); layernorm(x, nullptr, L.ln3.g, L.ln3.b, h, n, d, s, &pend); }
+    RUN(9) { OP(9); linear(h, n, d, L.fc1, 4 * d, mlp, 4 * d, 0, 1, nullptr, 0, 0, s); }
+    RUN(10) { OP(10); pend = residual_linear(e, mlp, n, 4 * d, L.fc2, x, s); }
   }
   e->pending = pend;  // folded in by the final LayerNorm (logits_for_rows)
 }
@@ -434,12 +463,12 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
 void logits_for_rows(b200w_engine* e, const int* sel_rows_dev, int n_sel, cudaStream_t s) {
   B200W_REQUIRE(n_sel <= e->logit_rows, "logits buffer too small");
   bf16* hsel = e->d_hsel.as<bf16>();
-  { OP(14); layernorm(e->d_x.as<float>(), sel_rows_dev, e->dec_ln.g, e->dec_ln.b, hsel, n_sel, e->d, s, &e->pending); }
+  RUN(14) { OP(14); layernorm(e->d_x.as<float>(), sel_rows_dev, e->dec_ln.g, e->dec_ln.b, hsel, n_sel, e->d, s, &e->pending); }
   if (!sel_rows_dev) e->pending = SplitReduce{};  // written back into x: must not be added twice
   Lin emb;
   emb.w = e->tok_emb;
   emb.b = nullptr;
-  { OP(11); linear(hsel, n_sel, e->d, emb, e->V, e->logits.p, e->ldv, 1, 0, nullptr, 0, 0, s); }
+  RUN(11) { OP(11); linear(hsel, n_sel, e->d, emb, e->V, e->logits.p, e->ldv, 1, 0, nullptr, 0, 0, s); }
 }
 
 void upload_ints(int* dst, const std::vector<int>& v, cudaStream_t s) {
@@ -829,7 +858,6 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
   // ---- autoregressive steps.  Fixed shape: row r = b*K + k for every (stream, beam slot), whether
   // it is live or not (idle rows decode a dummy token into a scratch slot), so that every step
   // issues the same launches on the same buffers and can be replayed as a CUDA graph.
-  const int n_rows = B * K;
   const int opts_hash = o.eot * 31 + o.timestamp_begin * 17 + o.max_initial_timestamp_index * 7 + k_top +
                         (o.without_timestamps ? 1000003 : 0);
   B200W_CHECK_CUDA(cudaMemsetAsync(e->tables[cur ^ 1].p, 0, (size_t)e->cfg.max_batch * e->cfg.max_beam * Tctx * 4, s));
@@ -842,7 +870,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     logits_for_rows(e, nullptr, m.n, s);
     SampleParams sps = sp;
     sps.state = m.state;
-    { OP(12); sample_topk(sps, m.n, s); }
+    RUN(12) { OP(12); sample_topk(sps, m.n, s); }
     B200W_CHECK_CUDA(cudaMemcpyAsync(h_ids, sp.out_ids, (size_t)m.n * k_top * 4, cudaMemcpyDeviceToHost, s));
     B200W_CHECK_CUDA(cudaMemcpyAsync(h_lp, sp.out_logprobs, (size_t)m.n * k_top * 4, cudaMemcpyDeviceToHost, s));
   };
@@ -912,6 +940,9 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     cur ^= 1;
     B200W_CHECK_CUDA(cudaStreamSynchronize(s));
     t_gpu += ms_since(t_s1);
+    if (ablate_mask() != 0)  // timing-only runs: keep every beam alive whatever the (garbage) logits say
+      for (int r = 0; r < B * K; ++r)
+        for (int c = 0; c < k_top; ++c) { h_ids[r * k_top + c] = 1000 + c; h_lp[r * k_top + c] = -1.f - c; }
     const auto t_s2 = now();
 
     // host-side beam bookkeeping

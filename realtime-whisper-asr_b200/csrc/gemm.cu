@@ -38,7 +38,15 @@ struct GemmParams {
   int hm_T, hm_d;  // head-major scatter of the output (cross K/V layout) when hm_T > 0
   int splits;      // split-K: > 1 => split s writes its partial sums (fp32) to out + s * split_stride
   long long split_stride;
+  long long* trace;  // development aid (b200w_gemm_set_trace): 16 timestamps per CTA, or null
 };
+
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define GEMM_TRACE(slot) do { if (p.trace) p.trace[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
 
 // 32 accumulator columns of one output row -> global memory.
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int b,
@@ -142,6 +150,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  if (p.trace && threadIdx.x == 0) { p.trace[blockIdx.x * 16 + 0] = gtime_ns(); GEMM_TRACE(1); }
   const uint32_t full0 = smem_u32(bars);
   const uint32_t empty0 = smem_u32(bars + STAGES);
   const uint32_t tfull0 = smem_u32(bars + 2 * STAGES);
@@ -169,10 +179,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int mn_tiles = p.total_tiles / p.splits;
+  if (threadIdx.x == 0) GEMM_TRACE(2);
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
       uint32_t stage = 0, phase = 0;
+      // Programmatic dependent launch: the weights do not depend on the kernel before this one, so
+      // the first tile's weight tiles (up to a full ring) are requested while that kernel is still
+      // running; only the activation loads wait for it.
+      int pre = 0;
+      {
+        const int tile = blockIdx.x;  // grid <= total_tiles
+        const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+        const int n0 = (mn % p.n_tiles) * BN;
+        const int kb_lo = (int)((long long)p.total_kb * ks / p.splits);
+        const int kb_hi = (int)((long long)p.total_kb * (ks + 1) / p.splits);
+        pre = kb_hi - kb_lo < STAGES ? kb_hi - kb_lo : STAGES;
+        for (int i = 0; i < pre; ++i) {
+          const uint32_t fb = full0 + 8 * i;
+          mbar_arrive_expect_tx(fb, AS_BYTES + B_BYTES);
+          tma_load_3d(smem_u32(sB + i * B_BYTES), &tmB, fb, (kb_lo + i) * BK, n0, 0);
+        }
+      }
+      pdl_wait();
+      GEMM_TRACE(3);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
         const int nt = mn % p.n_tiles, mt = mn / p.n_tiles;
@@ -186,14 +216,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int t = 0; t < p.n_taps; ++t) {
           for (int kb = 0; kb < p.tap_kb[t]; ++kb, ++kbg) {
             if (kbg < kb_lo || kbg >= kb_hi) continue;
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t fb = full0 + 8 * stage;
-            mbar_arrive_expect_tx(fb, AS_BYTES + B_BYTES);
+            const bool b_done = pre > 0;  // weights of this k-block were requested ahead of the wait
+            if (!b_done) {
+              mbar_wait(empty0 + 8 * stage, phase ^ 1);
+              mbar_arrive_expect_tx(fb, AS_BYTES + B_BYTES);
+            } else {
+              --pre;
+            }
 #pragma unroll
             for (int mi = 0; mi < MP; ++mi)
               tma_load_3d(smem_u32(sA + stage * AS_BYTES + mi * A_BYTES), &tmA, fb, p.tap_col[t] + kb * BK,
                           r0 + mi * BM + p.tap_shift[t], b);
-            tma_load_3d(smem_u32(sB + stage * B_BYTES), &tmB, fb, kbg * BK, n0, 0);
+            if (!b_done) tma_load_3d(smem_u32(sB + stage * B_BYTES), &tmB, fb, kbg * BK, n0, 0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -212,6 +247,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
+          if (kb == 0 && tile == (int)blockIdx.x) GEMM_TRACE(4);
           const uint64_t bd = make_sw128_desc(smem_u32(sB + stage * B_BYTES));
 #pragma unroll
           for (int mi = 0; mi < MP; ++mi) {
@@ -224,10 +260,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
+        if (tile == (int)blockIdx.x) GEMM_TRACE(5);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {  // ---------------- epilogue warps 2..9 (TMEM lane quarter = warp % 4, column half = (warp-2)/4)
+    pdl_wait();  // residual reads / output writes must not overtake the kernel before this one
     const int q = warp & 3;
     constexpr int CW = BN / 2;  // columns per warp
     const int cbeg = ((warp - 2) >> 2) * CW;
@@ -239,6 +277,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n0 = nt * BN;
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
+      if (warp == 2 && lane == 0 && tile == (int)blockIdx.x) GEMM_TRACE(6);
 #pragma unroll 1
       for (int mi = 0; mi < MP; ++mi) {
         const int r = (mt % p.m_tiles_per_batch) * (BM * MP) + mi * BM + q * 32 + lane;
@@ -258,6 +297,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (warp == 2 && lane == 0) GEMM_TRACE(7);
   }
   tc_fence_before();
   __syncthreads();
@@ -265,6 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (p.trace && threadIdx.x == 0) { GEMM_TRACE(8); p.trace[blockIdx.x * 16 + 9] = gtime_ns(); }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -316,6 +357,8 @@ struct ProfSlot {
   cudaEvent_t beg, end;
   double flops;
 };
+static long long* g_trace = nullptr;
+void gemm_set_trace(void* dev_buf) { g_trace = static_cast<long long*>(dev_buf); }
 static int g_prof_bn = 0;  // 0 = off, else the BN class being timed
 static std::vector<ProfSlot> g_prof_slots;
 static size_t g_prof_used = 0;
@@ -371,7 +414,7 @@ static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmPara
     ps = prof_slot(2.0 * (double)p.out_rows * p.batches * (double)p.N * (double)p.total_kb * BK);
     B200W_CHECK_CUDA(cudaEventRecord(ps->beg, stream));
   }
-  gemm_tcgen05_kernel<BN, STAGES, MP><<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  launch_pdl(gemm_tcgen05_kernel<BN, STAGES, MP>, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, tmA, tmB, p);
   if (ps) B200W_CHECK_CUDA(cudaEventRecord(ps->end, stream));
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
@@ -425,6 +468,7 @@ void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   // split-K: every split stores its fp32 partial sums in its own slab of `out`
   // ([splits][rows][out_row_stride]); the consumer (LayerNorm) adds the slabs in a fixed order, so
   // results do not depend on scheduling.  Bias / activation / residual are the consumer's job.
+  p.trace = g_trace;
   p.splits = d.split_k > 1 ? d.split_k : 1;
   p.split_stride = d.split_stride;
   B200W_REQUIRE(p.splits == 1 || (d.out_fp32 && !d.bias && !d.residual && d.act == 0 && d.n_taps == 0 &&

@@ -56,6 +56,9 @@ void conv1d_k3(const bf16* x, const bf16* w, const float* bias, const float* add
 void gemm_profile_begin(int bn);
 void gemm_profile_end(double* total_ms, double* total_flops, long long* launches);
 
+// Development aid: every CTA of later GEMM launches writes 16 int64 timestamps to dev_buf (null = off).
+void gemm_set_trace(void* dev_buf);
+
 // Build a 128B-swizzled TMA descriptor over a bf16 tensor viewed as [d2][d1][d0] (d0 contiguous).
 void make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                        uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1);

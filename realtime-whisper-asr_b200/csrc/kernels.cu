@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
   __shared__ float s_red[32];
   __shared__ float s_cv[32];
   __shared__ int s_ci[32];
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x, tid = threadIdx.x;
   float* lg = const_cast<float*>(p.logits) + (long long)row * p.ld;
   const int4 st = p.state[row];
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
 void sample_topk(const SampleParams& p, int rows, cudaStream_t stream) {
   if (rows <= 0) return;
   B200W_REQUIRE(p.k >= 1 && p.k <= MAX_TOPK, "top-k out of range");
-  sample_kernel<<<rows, SAMPLE_THREADS, 0, stream>>>(p);
+  launch_pdl(sample_kernel, dim3(rows), dim3(SAMPLE_THREADS), 0, stream, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }
