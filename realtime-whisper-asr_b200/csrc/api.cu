@@ -43,7 +43,8 @@ int b200w_abi_version(void) { return B200W_ABI_VERSION; }
 uint64_t b200w_launch_count(void) { return g_launch_count; }
 
 int b200w_gemm_set_trace(void* dev_buf) {
-  gemm_set_trace(dev_buf);
+  if (getenv("B200W_TRACE_CROSS")) cross_tc_set_trace(dev_buf);
+  else gemm_set_trace(dev_buf);
   return 0;
 }
 

@@ -806,11 +806,18 @@ static void launch_cross_split(const CrossAttnParams& p, int n_groups, int n_hea
 //   O[128 x 64]   += P[128 x 128 keys] . V_tile[128 keys x 64]   (rows >= 8 of P are don't-care: a
 //   row of A only feeds the same row of D, so the operand tile may overlap unrelated shared memory)
 // Warps 0-3: Q staging, softmax, output.  Warp 4: TMA producer.  Warp 5: MMA issuer.
-static constexpr int XT_RING = 12;
+// Load balance: with I items on G CTAs, floor(I/G) rounds of whole items are followed by one round
+// in which each of the remaining r items is cut into s <= G/r key ranges (s divides the tile count);
+// the pieces leave un-normalised partial results in global scratch and the last piece to finish
+// (atomic counter, self-resetting) merges them.  640 items on 148 SMs: 4 + 1/3 rounds instead of 5.
+static constexpr int XT_RING = 5;    // 16 KB slots; two CTAs share an SM and cover each other's softmax phases
 static constexpr int XT_MAX_TILES = 12;  // keys <= 1536
 static constexpr int XT_P_BYTES = XT_MAX_TILES * 2 * 1024;
 static constexpr int XT_Q_BYTES = 2048;
 static constexpr int XT_SMEM = XT_P_BYTES + XT_Q_BYTES + XT_RING * TILE_BYTES + 512 + 1024;
+static constexpr int XT_MAX_PIECES = 6;
+static constexpr int XT_CTAS_PER_SM = 2;
+static constexpr int XT_PART_FLOATS = 8 * 64 + 16;  // O[8][64], m[8], l[8]
 
 struct CrossTcParams {
   const bf16* q;
@@ -826,9 +833,118 @@ struct CrossTcParams {
   bf16* out;
   int out_stride;
   float scale_log2e;
+  float* partial;  // [grid][XT_MAX_PIECES][XT_PART_FLOATS]
+  int* counters;   // [grid], zero between launches
+  long long* trace;  // development aid: [cta][unit < 6][8] clock64 stamps, or null
 };
+#define XT_TRACE(slot) do { if (p.trace && it < 6) p.trace[(blockIdx.x * 6 + it) * 8 + (slot)] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(192, 1)
+struct XtUnit {
+  int item, t0, t1, piece, n_pieces, tail_idx;
+};
+// u-th unit of this CTA (every role evaluates the same sequence)
+__device__ __forceinline__ bool xt_unit(int u, int n_items, int n_tiles, XtUnit& un) {
+  const int G = gridDim.x, R = n_items / G, r = n_items - R * G;
+  if (u < R) {
+    un.item = blockIdx.x + u * G;
+    un.t0 = 0; un.t1 = n_tiles; un.piece = 0; un.n_pieces = 1; un.tail_idx = 0;
+    return true;
+  }
+  if (u > R || r == 0) return false;
+  int s = 1;
+  for (int d = 2; d <= XT_MAX_PIECES; ++d)
+    if (n_tiles % d == 0 && d * r <= G) s = d;
+  if ((int)blockIdx.x >= r * s) return false;
+  un.tail_idx = blockIdx.x / s;
+  un.piece = blockIdx.x - un.tail_idx * s;
+  un.n_pieces = s;
+  un.item = R * G + un.tail_idx;
+  const int tpp = n_tiles / s;
+  un.t0 = un.piece * tpp;
+  un.t1 = un.t0 + tpp;
+  return true;
+}
+
+// Softmax of one unit for the 128 softmax threads.  Thread = key row of every tile; NQ query columns
+// per tile are read from TMEM four tiles at a time (twice: once for the max, once for the
+// exponentials) to stay inside 168 registers.  Leaves P (bf16, K-major operand tiles, row = query,
+// column = key) in shared memory, per-warp maxima in s_red[0..32) and per-warp sums in s_red[32..64).
+// Rows of dead queries (q >= NQ) keep stale values: they only feed output rows nobody reads.
+template <int NQ>
+__device__ __forceinline__ void xt_softmax(const int len, const float scale_log2e, uint32_t tS, uint8_t* sP,
+                                           float* s_red, int t0, int nt) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int key0 = t0 * 128 + tid;
+  float mx[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) mx[q] = -INFINITY;
+#pragma unroll 1
+  for (int jc = 0; jc < nt; jc += 4) {
+    uint32_t sc[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (jc + j < nt) tmem_ld8(tS + 16 * (jc + j), sc[j]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (jc + j < nt && key0 + (jc + j) * 128 < len) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) mx[q] = fmaxf(mx[q], __uint_as_float(sc[j][q]));
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    for (int o = 16; o > 0; o >>= 1) mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
+  }
+  if (lane < 8) {
+    float v = mx[0];
+#pragma unroll
+    for (int q = 1; q < NQ; ++q) v = lane == q ? mx[q] : v;
+    s_red[warp * 8 + lane] = v;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  float sum[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const float m = fmaxf(fmaxf(s_red[q], s_red[8 + q]), fmaxf(s_red[16 + q], s_red[24 + q]));
+    mx[q] = m * scale_log2e;
+    sum[q] = 0.f;
+  }
+  const int kc = tid & 63, half = tid >> 6;
+  uint8_t* prow = sP + half * 1024 + (kc & 7) * 2;
+#pragma unroll 1
+  for (int jc = 0; jc < nt; jc += 4) {
+    uint32_t sc[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (jc + j < nt) tmem_ld8(tS + 16 * (jc + j), sc[j]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (jc + j < nt) {
+        const bool valid = key0 + (jc + j) * 128 < len;
+        uint8_t* pt = prow + (jc + j) * 2048;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float e = valid ? ex2_approx(fmaf(__uint_as_float(sc[j][q]), scale_log2e, -mx[q])) : 0.f;
+          sum[q] += e;
+          *reinterpret_cast<bf16*>(pt + q * 128 + (((kc >> 3) ^ q) << 4)) = __float2bfloat16(e);
+        }
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    for (int o = 16; o > 0; o >>= 1) sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
+  }
+  if (lane < 8) {
+    float v = sum[0];
+#pragma unroll
+    for (int q = 1; q < NQ; ++q) v = lane == q ? sum[q] : v;
+    s_red[32 + warp * 8 + lane] = v;
+  }
+}
+
+__global__ void __launch_bounds__(192, 2)
 cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -867,15 +983,16 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
   // K/V and the pass metadata were written long before the kernel ahead of this one started, so the
   // producer may run ahead of the dependency wait; Q (read) and the output (written) may not.
   const int n_items = *p.n_live_groups * p.n_heads;
+  XtUnit un;
 
   if (warp == 4) {
-    if (lane == 0) {  // ---------------- TMA producer: K tiles then V tiles of every item
+    if (lane == 0) {  // ---------------- TMA producer: K tiles then V tiles of every unit
       uint32_t slot = 0, phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int g = item / p.n_heads, h = item - g * p.n_heads;
+      for (int u = 0; xt_unit(u, n_items, n_tiles, un); ++u) {
+        const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
         const int blk = p.stream[p.g_start[g]] * p.blocks_per_stream + p.layer_block0 + h;
         for (int kv = 0; kv < 2; ++kv)
-          for (int j = 0; j < n_tiles; ++j) {
+          for (int j = un.t0; j < un.t1; ++j) {
             mbar_wait(empty0 + 8 * slot, phase ^ 1);
             const uint32_t fb = full0 + 8 * slot;
             mbar_arrive_expect_tx(fb, TILE_BYTES);
@@ -888,12 +1005,13 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
     if (lane == 0) {  // ---------------- MMA issuer
       constexpr uint32_t idescS = make_idesc_bf16(128, 16, 0, 0);  // K (K-major) x Q (K-major)
       constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);  // P (K-major) x V (MN-major)
-      uint32_t slot = 0, phase = 0, it = 0;
+      uint32_t slot = 0, phase = 0;
       const uint64_t qd = make_sw128_desc(smem_u32(sQ));
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      for (int it = 0; xt_unit(it, n_items, n_tiles, un); ++it) {
+        const int nt = un.t1 - un.t0;
         mbar_wait(bar_q, it & 1);
         tc_fence_after();
-        for (int j = 0; j < n_tiles; ++j) {
+        for (int j = 0; j < nt; ++j) {
           mbar_wait(full0 + 8 * slot, phase);
           tc_fence_after();
           const uint64_t kd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
@@ -905,7 +1023,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
         tc_commit(bar_s);
         mbar_wait(bar_p, it & 1);
         tc_fence_after();
-        for (int j = 0; j < n_tiles; ++j) {
+        for (int j = 0; j < nt; ++j) {
           mbar_wait(full0 + 8 * slot, phase);
           tc_fence_after();
           const uint64_t vd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
@@ -923,10 +1041,10 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
   } else {  // ---------------- warps 0..3: Q staging, softmax (thread = key row of every tile), output
     pdl_wait();
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int g = item / p.n_heads, h = item - g * p.n_heads;
+    for (int it = 0; xt_unit(it, n_items, n_tiles, un); ++it) {
+      const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
       const int q0 = p.g_start[g], nq = p.g_count[g];
+      const int nt = un.t1 - un.t0;
       {  // Q -> swizzled K-major [16][64] tile (rows >= nq zero)
         const int qr = tid >> 3, ch = tid & 7;
         uint4 u = make_uint4(0u, 0u, 0u, 0u);
@@ -935,97 +1053,108 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
       }
       fence_proxy_async_smem();
       mbar_arrive(bar_q);
+      if (tid == 0) XT_TRACE(0);
       mbar_wait(bar_s, it & 1);
       tc_fence_after();
-      // scores of this thread's key in every tile, 8 query columns each
-      uint32_t sc[XT_MAX_TILES][8];
-#pragma unroll
-      for (int j = 0; j < XT_MAX_TILES; ++j)
-        if (j < n_tiles) tmem_ld8(tmem_S + lane_sel + 16 * j, sc[j]);
-      tmem_ld_wait();
-      float mx[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) mx[q] = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < XT_MAX_TILES; ++j)
-        if (j < n_tiles && j * 128 + tid < p.len) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) mx[q] = fmaxf(mx[q], __uint_as_float(sc[j][q]));
-        }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        for (int o = 16; o > 0; o >>= 1) mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
-      }
-      if (lane < 8) {
-        float v = mx[0];
-#pragma unroll
-        for (int q = 1; q < 8; ++q) v = lane == q ? mx[q] : v;
-        s_red[warp * 8 + lane] = v;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float sum[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float m = fmaxf(fmaxf(s_red[q], s_red[8 + q]), fmaxf(s_red[16 + q], s_red[24 + q]));
-        mx[q] = m * p.scale_log2e;
-        sum[q] = 0.f;
-      }
-      // P = exp2(s * c - m * c) as bf16 into the K-major operand tiles (row = query, column = key)
-      const int kc = tid & 63, half = tid >> 6;
-      uint8_t* prow = sP + half * 1024 + (kc & 7) * 2;
-#pragma unroll
-      for (int j = 0; j < XT_MAX_TILES; ++j)
-        if (j < n_tiles) {
-          const bool valid = j * 128 + tid < p.len;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float e = valid ? ex2_approx(fmaf(__uint_as_float(sc[j][q]), p.scale_log2e, -mx[q])) : 0.f;
-            sum[q] += e;
-            *reinterpret_cast<bf16*>(prow + j * 2048 + q * 128 + (((kc >> 3) ^ q) << 4)) = __float2bfloat16(e);
-          }
-        }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        for (int o = 16; o > 0; o >>= 1) sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
-      }
-      if (lane < 8) {
-        float v = sum[0];
-#pragma unroll
-        for (int q = 1; q < 8; ++q) v = lane == q ? sum[q] : v;
-        s_red[32 + warp * 8 + lane] = v;
-      }
+      if (tid == 0) XT_TRACE(1);
+      // softmax over the unit's keys, specialised on the number of live queries (branch-free inner loops)
+      if (nq <= 1) xt_softmax<1>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, s_red, un.t0, nt);
+      else if (nq <= 2) xt_softmax<2>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, s_red, un.t0, nt);
+      else if (nq <= 5) xt_softmax<5>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, s_red, un.t0, nt);
+      else xt_softmax<8>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, s_red, un.t0, nt);
+      if (tid == 0) XT_TRACE(7);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
+      if (tid == 0) XT_TRACE(2);
       mbar_wait(bar_o, it & 1);
       tc_fence_after();
+      if (tid == 0) XT_TRACE(3);
       if (warp == 0) {
-        uint32_t o0[32], o1[32];
-        tmem_ld32(tmem_O, o0);
-        tmem_ld32(tmem_O + 32, o1);
-        tmem_ld_wait();
-        if (lane < nq) {
-          // the other warps' partial sums were stored before their arrive on bar_p, which bar_o follows
-          const float inv = 1.0f / (s_red[32 + lane] + s_red[40 + lane] + s_red[48 + lane] + s_red[56 + lane]);
-          bf16* dst = p.out + (long long)(q0 + lane) * p.out_stride + h * HD;
+        // the other warps' partial sums were stored before their arrive on bar_p, which bar_o follows
+        const float lsum = lane < 8 ? s_red[32 + lane] + s_red[40 + lane] + s_red[48 + lane] + s_red[56 + lane] : 1.f;
+        float* rec = p.partial + ((long long)un.tail_idx * XT_MAX_PIECES + un.piece) * XT_PART_FLOATS;
+        const float inv = 1.0f / lsum;
+#pragma unroll 1
+        for (int hc = 0; hc < 2; ++hc) {  // 32 output dims at a time (lane = query row)
+          uint32_t o[32];
+          tmem_ld32(tmem_O + 32 * hc, o);
+          tmem_ld_wait();
+          if (un.n_pieces == 1) {
+            if (lane < nq) {
+              bf16* dst = p.out + (long long)(q0 + lane) * p.out_stride + h * HD + 32 * hc;
 #pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            uint4 u, w;
-            __nv_bfloat162* u2 = reinterpret_cast<__nv_bfloat162*>(&u);
-            __nv_bfloat162* w2 = reinterpret_cast<__nv_bfloat162*>(&w);
+              for (int c = 0; c < 32; c += 8) {
+                uint4 u;
+                __nv_bfloat162* u2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              u2[i] = __floats2bfloat162_rn(__uint_as_float(o0[c + 2 * i]) * inv, __uint_as_float(o0[c + 2 * i + 1]) * inv);
-              w2[i] = __floats2bfloat162_rn(__uint_as_float(o1[c + 2 * i]) * inv, __uint_as_float(o1[c + 2 * i + 1]) * inv);
+                for (int i = 0; i < 4; ++i)
+                  u2[i] = __floats2bfloat162_rn(__uint_as_float(o[c + 2 * i]) * inv, __uint_as_float(o[c + 2 * i + 1]) * inv);
+                *reinterpret_cast<uint4*>(dst + c) = u;
+              }
             }
-            *reinterpret_cast<uint4*>(dst + c) = u;
-            *reinterpret_cast<uint4*>(dst + 32 + c) = w;
+          } else if (lane < 8) {
+            // piece of a split item: un-normalised partial result -> scratch; the last piece merges
+            float4* dst = reinterpret_cast<float4*>(rec + lane * 64 + 32 * hc);
+#pragma unroll
+            for (int c = 0; c < 32; c += 4)
+              dst[c >> 2] = make_float4(__uint_as_float(o[c]), __uint_as_float(o[c + 1]), __uint_as_float(o[c + 2]),
+                                        __uint_as_float(o[c + 3]));
+          }
+        }
+        if (un.n_pieces > 1) {
+          if (lane < 8) {
+            rec[512 + lane] = fmaxf(fmaxf(s_red[lane], s_red[8 + lane]), fmaxf(s_red[16 + lane], s_red[24 + lane])) *
+                              p.scale_log2e;
+            rec[520 + lane] = lsum;
+          }
+          __threadfence();
+          __syncwarp();
+          int old = 0;
+          if (lane == 0) old = atomicAdd(p.counters + un.tail_idx, 1);
+          old = __shfl_sync(0xffffffffu, old, 0);
+          if (old == un.n_pieces - 1) {
+            __threadfence();
+            const float* base = p.partial + (long long)un.tail_idx * XT_MAX_PIECES * XT_PART_FLOATS;
+            const int q = lane >> 2, c0 = (lane & 3) * 16;  // lane -> (query, 16 dims)
+            float M = -INFINITY;
+            for (int s2 = 0; s2 < un.n_pieces; ++s2) M = fmaxf(M, __ldcg(base + s2 * XT_PART_FLOATS + 512 + q));
+            float L = 0.f, acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            for (int s2 = 0; s2 < un.n_pieces; ++s2) {
+              const float* r2 = base + s2 * XT_PART_FLOATS;
+              const float w = ex2_approx(__ldcg(r2 + 512 + q) - M);
+              L = fmaf(__ldcg(r2 + 520 + q), w, L);
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(r2 + q * 64 + c0 + i));
+                acc[i] = fmaf(v.x, w, acc[i]); acc[i + 1] = fmaf(v.y, w, acc[i + 1]);
+                acc[i + 2] = fmaf(v.z, w, acc[i + 2]); acc[i + 3] = fmaf(v.w, w, acc[i + 3]);
+              }
+            }
+            if (q < nq) {
+              const float invL = 1.0f / L;
+              bf16* dst = p.out + (long long)(q0 + q) * p.out_stride + h * HD + c0;
+              uint4 u, w4;
+              __nv_bfloat162* u2 = reinterpret_cast<__nv_bfloat162*>(&u);
+              __nv_bfloat162* w2 = reinterpret_cast<__nv_bfloat162*>(&w4);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                u2[i] = __floats2bfloat162_rn(acc[2 * i] * invL, acc[2 * i + 1] * invL);
+                w2[i] = __floats2bfloat162_rn(acc[8 + 2 * i] * invL, acc[8 + 2 * i + 1] * invL);
+              }
+              *reinterpret_cast<uint4*>(dst) = u;
+              *reinterpret_cast<uint4*>(dst + 8) = w4;
+            }
+            if (lane == 0) p.counters[un.tail_idx] = 0;  // ready for the next launch
           }
         }
       }
       tc_fence_before();
-      // s_red / sQ / sP are rewritten by the next item: everyone must be past their reads first
+      // s_red / sQ / sP are rewritten by the next unit: everyone must be past their reads first
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) XT_TRACE(4);
     }
   }
   tc_fence_before();
@@ -1036,9 +1165,16 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
   }
 }
 
+static long long* g_xt_trace = nullptr;
+void cross_tc_set_trace(void* dev_buf) { g_xt_trace = static_cast<long long*>(dev_buf); }
+
+size_t cross_attention_tc_scratch_bytes() {
+  return (size_t)XT_CTAS_PER_SM * num_sms() * (XT_MAX_PIECES * XT_PART_FLOATS * sizeof(float) + sizeof(int));
+}
+
 void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int layer, int n_heads, int len,
                         const bf16* q, int q_stride, const int* stream, const int* g_start, const int* g_count,
-                        const int* n_live_groups, int n_groups, bf16* out, int out_stride, float scale,
+                        const int* n_live_groups, int n_groups, bf16* out, int out_stride, float scale, void* scratch,
                         cudaStream_t cs) {
   if (n_groups <= 0) return;
   B200W_REQUIRE(len <= 128 * XT_MAX_TILES, "cross_attention_tc: at most 1536 keys");
@@ -1055,8 +1191,13 @@ void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int l
   p.n_live_groups = n_live_groups; p.n_heads = n_heads; p.blocks_per_stream = n_layers * 2 * n_heads;
   p.layer_block0 = 2 * layer * n_heads; p.len = len; p.out = out; p.out_stride = out_stride;
   p.scale_log2e = scale * 1.4426950408889634f;
+  // scratch: zero-initialised once by the owner; [num_sms counters][num_sms * pieces * record]
+  p.counters = static_cast<int*>(scratch);
+  p.partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + ((XT_CTAS_PER_SM * num_sms() * sizeof(int) + 255) & ~(size_t)255));
+  p.trace = g_xt_trace;
   const int items = n_groups * n_heads;
-  launch_pdl(cross_attn_tc_kernel, dim3(items < num_sms() ? items : num_sms()), dim3(192), (size_t)XT_SMEM, cs, tm, p);
+  const int max_ctas = XT_CTAS_PER_SM * num_sms();
+  launch_pdl(cross_attn_tc_kernel, dim3(items < max_ctas ? items : max_ctas), dim3(192), (size_t)XT_SMEM, cs, tm, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }

@@ -128,6 +128,7 @@ struct b200w_engine {
   DevBuf cross_off, const_len, mask, topk_ids, topk_lp, probs, head_export;
   DevBuf al_w, al_mat, al_trace, al_path, al_plen, scratch_i;
   DevBuf x_split;        // split-KV partial results of the decode-step cross attention
+  DevBuf x_tc;           // tensor-core cross attention: split-item partial results + arrival counters
   DevBuf d_split;        // fp32 split-K partial sums of the GEMM feeding the residual stream
   SplitReduce pending;   // partial sums of the last decoder GEMM, folded in by the next LayerNorm
   PinnedBuf h_meta, h_out;
@@ -446,7 +447,7 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
       OP(7);
       if (use_tc && !c.head_export && m.max_group <= CROSS_GROUP && m.n_groups <= 64)
         cross_attention_tc(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, d, m.stream, m.g_start, m.g_count,
-                           m.n_live, m.n_groups, attn, d, 0.125f, s);
+                           m.n_live, m.n_groups, attn, d, 0.125f, e->x_tc.p, s);
       else
         cross_attention(c, m.n_groups, e->H, m.max_group, s, e->x_split.as<float>());
     }
@@ -506,7 +507,7 @@ int b200w_engine_destroy(b200w_engine* e) {
                       &e->d_attn, &e->d_cq, &e->d_mlp, &e->d_hsel, &e->kpool, &e->vpool, &e->tables[0],
                       &e->tables[1], &e->logits, &e->meta, &e->cross_off, &e->const_len, &e->mask,
                       &e->topk_ids, &e->topk_lp, &e->probs, &e->head_export, &e->al_w, &e->al_mat,
-                      &e->al_trace, &e->al_path, &e->al_plen, &e->scratch_i, &e->d_split, &e->x_split};
+                      &e->al_trace, &e->al_path, &e->al_plen, &e->scratch_i, &e->d_split, &e->x_split, &e->x_tc};
     for (DevBuf* b : bufs) b->release();
     e->h_meta.release();
     e->h_out.release();
@@ -580,7 +581,9 @@ int b200w_engine_finalize(b200w_engine* e) {
   e->d_cq.alloc(n * d * 2);
   e->d_mlp.alloc(n * 4 * d * 2);
   e->d_split.alloc((size_t)(128 * 160 * 64) * 16 * 4);
-  e->x_split.alloc(cross_attention_scratch_bytes(64, e->H));  // splits only happen below ~148 tiles
+  e->x_split.alloc(cross_attention_scratch_bytes(64, e->H));
+  e->x_tc.alloc(cross_attention_tc_scratch_bytes() + 256);
+  B200W_CHECK_CUDA(cudaMemset(e->x_tc.p, 0, cross_attention_tc_scratch_bytes() + 256));  // splits only happen below ~148 tiles
   e->slots_per_stream = e->Tctx * e->cfg.max_beam;
   e->total_slots = (long long)e->slots_per_stream * Bm;
   e->kpool.alloc((size_t)e->Ld * e->total_slots * d * 2);

@@ -10,6 +10,7 @@ import sys
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--child", action="store_true")
+ap.add_argument("--ops", default="", help="comma-separated op ids (default: all)")
 a = ap.parse_args()
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if a.child:
@@ -32,7 +33,10 @@ if a.child:
 NAMES = {0: "none(1<<15)", 1: "layernorm", 2: "qkv_gemm", 3: "kv_scatter", 4: "self_attn", 5: "out_gemm", 6: "cq_gemm",
          7: "cross_attn", 8: "cout_gemm", 9: "fc1_gemm", 10: "fc2_gemm", 11: "logits_gemm", 12: "sample"}
 base = None
+sel = [0] + [int(x) for x in a.ops.split(',')] if a.ops else list(NAMES)
 for bit, name in NAMES.items():
+    if bit not in sel:
+        continue
     env = dict(os.environ, B200W_DECODE_TIMING="1", B200W_ABLATE=str(1 << (15 if bit == 0 else bit)))
     out = subprocess.run([sys.executable, __file__, "--child", "--steps", str(a.steps)], env=env,
                          capture_output=True, text=True)
