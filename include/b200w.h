@@ -84,6 +84,12 @@ int b200w_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev,
                     const void* residual_dev, void* out_dev, int M, int N, int K, int64_t lda,
                     int64_t ldw, int64_t ldr, int64_t ldo, int flags, int force_bn, void* stream);
 
+/* Decode-step (skinny) GEMM, M <= 256: out[M][N] = act(X[M][K] * W[N][K]^T + bias), weight rows on the
+ * MMA's M dimension (swap-AB), see csrc/skinny.cu.  flags: bit0 out fp32, bit2 GELU.  splits > 1: out
+ * receives fp32 partial sums [splits][M][ldo] (bias must be NULL, no GELU). */
+int b200w_skinny_gemm(const void* X_dev, const void* W_dev, const float* bias_dev, void* out_dev, int M, int N,
+                      int K, int64_t ldx, int64_t ldw, int64_t ldo, int flags, int splits, void* stream);
+
 /* conv1d (kernel 3, padding 1, stride 1 or 2) as implicit GEMM over time-major activations:
  * x bf16 [B][T][C] -> GELU(conv(x) + bias) (+ addend fp32 [T_out][N], e.g. positions) ->
  * out [B][T_out][N] bf16 or fp32.  w bf16 [N][3*C] tap-major.  C % 64 == 0. */

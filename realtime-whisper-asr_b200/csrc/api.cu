@@ -8,6 +8,7 @@
 #include "common.h"
 #include "frontend.h"
 #include "gemm.h"
+#include "skinny.h"
 
 namespace b200w {
 
@@ -18,7 +19,7 @@ void set_last_error(const std::string& s) { t_last_error = s; }
 const char* get_last_error() { return t_last_error.c_str(); }
 
 bool pdl_enabled() {
-  static const bool on = getenv("B200W_NO_PDL") == nullptr;
+  static const bool on = getenv("B200W_PDL") != nullptr;  // measured slightly slower inside the captured decode step: opt-in
   return on;
 }
 
@@ -44,6 +45,7 @@ uint64_t b200w_launch_count(void) { return g_launch_count; }
 
 int b200w_gemm_set_trace(void* dev_buf) {
   if (getenv("B200W_TRACE_CROSS")) cross_tc_set_trace(dev_buf);
+  else if (getenv("B200W_TRACE_SKINNY")) skinny_set_trace(dev_buf);
   else gemm_set_trace(dev_buf);
   return 0;
 }
@@ -122,6 +124,29 @@ int b200w_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev,
     d.split_stride = (int64_t)M * ldo;
   }
   gemm_bf16(d, static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
+int b200w_skinny_gemm(const void* X_dev, const void* W_dev, const float* bias_dev, void* out_dev, int M, int N,
+                      int K, int64_t ldx, int64_t ldw, int64_t ldo, int flags, int splits, void* stream) {
+  B200W_API_BEGIN
+  SkinnyDesc d;
+  d.X = static_cast<const bf16*>(X_dev);
+  d.ldx = ldx;
+  d.M = M;
+  d.W = static_cast<const bf16*>(W_dev);
+  d.ldw = ldw;
+  d.N = N;
+  d.K = K;
+  d.bias = bias_dev;
+  d.act = (flags & 4) ? 1 : 0;
+  d.out = out_dev;
+  d.out_fp32 = (flags & 1) ? 1 : 0;
+  d.ldo = ldo;
+  d.splits = splits & 0xff;
+  d.tile_rows = (splits >> 8) == 64 ? 64 : 128;  // test hook: bits 8.. of `splits` select 64-row tiles
+  d.split_stride = (int64_t)M * ldo;
+  skinny_gemm(d, static_cast<cudaStream_t>(stream));
   B200W_API_END
 }
 

@@ -23,6 +23,7 @@
 #include "common.h"
 #include "gemm.h"
 #include "kernels.h"
+#include "skinny.h"
 
 using namespace b200w;
 
@@ -143,6 +144,7 @@ struct b200w_engine {
   };
   std::vector<StepGraph> step_graphs;
   bool use_graphs = true;
+  bool step_pass = false;  // the pass being enqueued is a decode step (selects the skinny GEMM path)
   unsigned long long launches_per_step = 0;
   cudaStream_t own_stream = nullptr;  // decode runs here (the legacy default stream cannot be captured)
   cudaEvent_t join_event = nullptr;
@@ -257,8 +259,36 @@ static unsigned ablate_mask() {
 
 // x += A W^T + b for the decoder's residual stream.  Skinny calls (decode steps) are split along K so
 // that enough CTAs stream the weights; the partial sums are handed to the next LayerNorm.
+// Decode steps (at most 256 rows): weight-row-major tcgen05 GEMM (skinny.cu), split along K into fp32 slabs
+// in e->d_split that the consumer reduces.  Returns the slab description.
+static bool use_skinny() {
+  static const bool on = getenv("B200W_NO_SKINNY") == nullptr;
+  return on;
+}
+SplitReduce skinny_split(b200w_engine* e, const bf16* A, int M, int K, const Lin& l, int N, int max_splits,
+                         cudaStream_t s) {
+  const int splits = std::max(2, skinny_suggest_splits(N, K, max_splits));
+  B200W_REQUIRE((size_t)splits * M * N * 4 <= e->d_split.bytes, "split buffer too small");
+  // more than 256 rows: one launch per 256-row chunk (each row's arithmetic does not depend on the chunking)
+  for (int r0 = 0; r0 < M; r0 += 256) {
+    SkinnyDesc g;
+    g.X = A + (long long)r0 * K; g.ldx = K; g.M = std::min(256, M - r0);
+    g.W = l.w; g.ldw = K; g.N = N; g.K = K;
+    g.out = e->d_split.as<float>() + (long long)r0 * N; g.out_fp32 = 1; g.ldo = N;
+    g.splits = splits; g.split_stride = (int64_t)M * N;
+    skinny_gemm(g, s);
+  }
+  SplitReduce r;
+  r.partial = e->d_split.as<float>();
+  r.n = splits;
+  r.stride = (long long)M * N;
+  r.bias = l.b;
+  return r;
+}
+
 SplitReduce residual_linear(b200w_engine* e, const bf16* A, int M, int K, const Lin& l, float* x, cudaStream_t s) {
   const int d = e->d;
+  if (use_skinny() && e->step_pass && d % 128 == 0) return skinny_split(e, A, M, K, l, d, 14, s);
   const int splits = gemm_suggest_splits(M, d, K);
   if (splits <= 1 || (size_t)splits * M * d * 4 > e->d_split.bytes) {
     linear(A, M, K, l, d, x, d, 1, 0, x, 1, d, s);
@@ -413,8 +443,19 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     bf16* vp = e->vpool.as<bf16>() + (long long)l * e->total_slots * d;
     // self attention
     RUN(1) { OP(1); layernorm(x, nullptr, L.ln1.g, L.ln1.b, h, n, d, s, &pend); }
-    RUN(2) { OP(2); linear(h, n, d, L.qkv, 3 * d, qkv, 3 * d, 0, 0, nullptr, 0, 0, s); }
-    RUN(3) { OP(3); kv_scatter(qkv, m.slot, kp, vp, n, d, s); }
+    // decode steps only: the choice must not depend on how many streams are batched (batch invariance)
+    const bool sk = use_skinny() && e->step_pass && d % 128 == 0;
+    if (sk) {
+      // split-K QKV projection; the reduction adds the bias, rounds to bf16 and scatters K / V into the cache
+      RUN(2) {
+        OP(2);
+        const SplitReduce r = skinny_split(e, h, n, d, L.qkv, 3 * d, 4, s);
+        split_finalize(r.partial, r.n, r.stride, r.bias, n, 3 * d, 0, qkv, 3 * d, m.slot, kp, vp, d, s);
+      }
+    } else {
+      RUN(2) { OP(2); linear(h, n, d, L.qkv, 3 * d, qkv, 3 * d, 0, 0, nullptr, 0, 0, s); }
+      RUN(3) { OP(3); kv_scatter(qkv, m.slot, kp, vp, n, d, s); }
+    }
     DecAttnParams a;
     a.q = qkv; a.q_stride = 3 * d;
     a.kbase = kp; a.vbase = vp; a.kv_row_stride = d;
@@ -424,7 +465,15 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     RUN(5) { OP(5); pend = residual_linear(e, attn, n, d, L.out, x, s); }
     // cross attention
     RUN(1) { OP(1); layernorm(x, nullptr, L.ln2.g, L.ln2.b, h, n, d, s, &pend); }
-    RUN(6) { OP(6); linear(h, n, d, L.cq, d, cq, d, 0, 0, nullptr, 0, 0, s); }
+    RUN(6) {
+      OP(6);
+      if (sk) {
+        const SplitReduce r = skinny_split(e, h, n, d, L.cq, d, 10, s);
+        split_finalize(r.partial, r.n, r.stride, r.bias, n, d, 0, cq, d, nullptr, nullptr, nullptr, 0, s);
+      } else {
+        linear(h, n, d, L.cq, d, cq, d, 0, 0, nullptr, 0, 0, s);
+      }
+    }
     CrossAttnParams c;
     c.q = cq; c.q_stride = d;
     // cross K/V layout [stream][layer][k|v][head][1500][64]
@@ -454,7 +503,21 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     RUN(8) { OP(8); pend = residual_linear(e, attn, n, d, L.cout, x, s); }
     // MLP
     RUN(1) { OP(1); layernorm(x, nullptr, L.ln3.g, L.ln3.b, h, n, d, s, &pend); }
-    RUN(9) { OP(9); linear(h, n, d, L.fc1, 4 * d, mlp, 4 * d, 0, 1, nullptr, 0, 0, s); }
+    RUN(9) {
+      OP(9);
+      if (sk) {
+        for (int r0 = 0; r0 < n; r0 += 256) {
+          SkinnyDesc g;
+          g.X = h + (long long)r0 * d; g.ldx = d; g.M = std::min(256, n - r0);
+          g.W = L.fc1.w; g.ldw = d; g.N = 4 * d; g.K = d;
+          g.bias = L.fc1.b; g.act = 1;
+          g.out = mlp + (long long)r0 * 4 * d; g.out_fp32 = 0; g.ldo = 4 * d;
+          skinny_gemm(g, s);
+        }
+      } else {
+        linear(h, n, d, L.fc1, 4 * d, mlp, 4 * d, 0, 1, nullptr, 0, 0, s);
+      }
+    }
     RUN(10) { OP(10); pend = residual_linear(e, mlp, n, 4 * d, L.fc2, x, s); }
   }
   e->pending = pend;  // folded in by the final LayerNorm (logits_for_rows)
@@ -580,7 +643,13 @@ int b200w_engine_finalize(b200w_engine* e) {
   B200W_CHECK_CUDA(cudaMemset(e->d_attn.p, 0, n * d * 2));  // padding rows are never written: keep them finite
   e->d_cq.alloc(n * d * 2);
   e->d_mlp.alloc(n * 4 * d * 2);
-  e->d_split.alloc((size_t)(128 * 160 * 64) * 16 * 4);
+  {
+    // split-K slabs: the old path (at most 16 slabs of [256 rows][d]) and the decode-step path
+    // (14 slabs of [rows][d] or 4 slabs of [rows][3d], rows = max_batch * max_beam)
+    const size_t step_rows = (size_t)Bm * e->cfg.max_beam;
+    const size_t need = std::max<size_t>((size_t)(128 * 160 * 64) * 16 * 4, 16 * step_rows * (size_t)d * 4);
+    e->d_split.alloc(need);
+  }
   e->x_split.alloc(cross_attention_scratch_bytes(64, e->H));
   e->x_tc.alloc(cross_attention_tc_scratch_bytes() + 256);
   B200W_CHECK_CUDA(cudaMemset(e->x_tc.p, 0, cross_attention_tc_scratch_bytes() + 256));  // splits only happen below ~148 tiles
@@ -869,7 +938,14 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     // fork the page tables: new[row] = old[parent][0:pos] + [slot]
     gather_fork_tables(e->tables[from].as<int>(), m.parent, m.trow, m.pos, m.slot, e->tables[from ^ 1].as<int>(),
                        m.n, Tctx, s);
-    decoder_forward(e, ckv, m, e->tables[from ^ 1].as<int>(), Tctx, nullptr, s);
+    e->step_pass = true;
+    try {
+      decoder_forward(e, ckv, m, e->tables[from ^ 1].as<int>(), Tctx, nullptr, s);
+    } catch (...) {
+      e->step_pass = false;
+      throw;
+    }
+    e->step_pass = false;
     logits_for_rows(e, nullptr, m.n, s);
     SampleParams sps = sp;
     sps.state = m.state;

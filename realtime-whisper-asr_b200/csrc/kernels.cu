@@ -7,6 +7,21 @@
 
 namespace b200w {
 
+// exact-erf GELU (Abramowitz-Stegun 7.1.26), same arithmetic as the GEMM epilogue (ptx.cuh)
+__device__ __forceinline__ float gelu_erf_k(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
 // ------------------------------------------------------------------------------- LayerNorm
 // one warp per row; x fp32 (optionally gathered through row_idx) -> y bf16.  d % 128 == 0, d <= 1280.
 // Optional fused split-K reduce: x[row] += bias + sum_s partial[s][row] (slabs added in order) before
@@ -197,6 +212,51 @@ void kv_scatter(const bf16* qkv, const int* slot, bf16* kpool, bf16* vpool, int 
                 cudaStream_t stream) {
   if (n <= 0) return;
   launch_pdl(kv_scatter_kernel, dim3(n), dim3(128), 0, stream, qkv, slot, kpool, vpool, d);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------- split-K finalize
+// out[row][c] = bf16(act(bias[c] + sum_s partial[s][row][c])) for GEMMs whose consumer is not a LayerNorm
+// (slabs added in order: deterministic).  With slot != null the row is a fused QKV projection: columns
+// [0, d) (Q) go to out, [d, 2d) to kpool[slot[row]], [2d, 3d) to vpool[slot[row]] -- the KV-cache scatter
+// of the decode step folded into the reduction.
+__global__ void __launch_bounds__(256) split_finalize_kernel(const float* __restrict__ partial, int n_splits,
+                                                             long long stride, const float* __restrict__ bias, int N,
+                                                             int act, bf16* __restrict__ out, long long ldo,
+                                                             const int* __restrict__ slot, bf16* __restrict__ kpool,
+                                                             bf16* __restrict__ vpool, int d) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (c >= N) return;
+  const float* pp = partial + (long long)row * N + c;
+  float4 a = __ldg(reinterpret_cast<const float4*>(bias + c));
+#pragma unroll 4
+  for (int s = 0; s < n_splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(pp + s * stride);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  if (act == 1) { a.x = gelu_erf_k(a.x); a.y = gelu_erf_k(a.y); a.z = gelu_erf_k(a.z); a.w = gelu_erf_k(a.w); }
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  bf16* dst = out + (long long)row * ldo + c;
+  if (slot && c >= d) {
+    const long long sl = slot[row];
+    dst = c < 2 * d ? kpool + sl * d + (c - d) : vpool + sl * d + (c - 2 * d);
+  }
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+
+void split_finalize(const float* partial, int n_splits, long long stride, const float* bias, int rows, int N, int act,
+                    bf16* out, long long ldo, const int* slot, bf16* kpool, bf16* vpool, int d, cudaStream_t stream) {
+  if (rows <= 0) return;
+  B200W_REQUIRE(N % 4 == 0 && ldo % 4 == 0 && (!slot || d % 4 == 0), "split_finalize: widths must be multiples of 4");
+  launch_pdl(split_finalize_kernel, dim3(rows, cdiv(N / 4, 256)), dim3(256), 0, stream, partial, n_splits, stride, bias, N,
+             act, out, ldo, slot, kpool, vpool, d);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }

@@ -19,6 +19,11 @@ void embed_tokens(const int* tok, const int* pos, const bf16* tok_emb, const flo
 void kv_scatter(const bf16* qkv, const int* slot, bf16* kpool, bf16* vpool, int n, int d,
                 cudaStream_t stream);
 
+// Reduce split-K slabs of a GEMM whose consumer is not a LayerNorm: out = bf16(act(bias + sum of slabs)).
+// slot != null: fused-QKV rows, K and V columns are scattered into the KV-cache pools instead.
+void split_finalize(const float* partial, int n_splits, long long stride, const float* bias, int rows, int N, int act,
+                    bf16* out, long long ldo, const int* slot, bf16* kpool, bf16* vpool, int d, cudaStream_t stream);
+
 // per-row sampling state flags (state[row].x); state[row].y = lowest admissible timestamp id
 enum : int {
   SF_RULES = 1,       // apply Whisper timestamp rules

@@ -97,3 +97,38 @@ def test_enc_attention(lib, cuda_device, B, T, H):
     ref = ref.transpose(1, 2).reshape(B, T, d)
     err = (out.float() - ref).abs().max().item()
     assert err <= 2e-2, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("M,N,K,splits", [
+    (160, 1280, 1280, 1), (160, 1280, 1280, 10), (160, 3840, 1280, 4), (160, 1280, 5120, 14), (160, 5120, 1280, 1),
+    (5, 1280, 1280, 8), (1, 384, 384, 1), (37, 1000, 512, 3), (256, 768, 768, 2), (160, 51866, 1280, 1),
+    (160, 1280, 1280, 5 | (64 << 8)), (160, 3840, 1280, 2 | (64 << 8)), (64, 1000, 512, 1 | (64 << 8)),
+])
+def test_skinny_gemm(lib, cuda_device, M, N, K, splits):
+    """Decode-step GEMM (weight rows on the MMA M dimension) vs torch fp32; split-K slabs summed in order."""
+    g = torch.Generator(device="cpu").manual_seed(M * 5 + N + K + splits)
+    X = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(cuda_device)
+    ldo = (N + 7) // 8 * 8
+    ref = X.float() @ W.float().T
+    tol = 2e-3 * max(1.0, ref.abs().max().item())
+    s = torch.cuda.current_stream().cuda_stream
+    tile64 = splits & (64 << 8)  # bits 8.. of the `splits` argument select 64-row weight tiles (test hook)
+    splits &= 0xff
+    if splits > 1:
+        out = torch.zeros((splits, M, ldo), dtype=torch.float32, device=cuda_device)
+        _lib.check(lib.b200w_skinny_gemm(X.data_ptr(), W.data_ptr(), None, out.data_ptr(), M, N, K, K, K, ldo, 1, splits | tile64, s))
+        torch.cuda.synchronize()
+        got = out.sum(0)[:, :N]
+        assert (got - ref).abs().max().item() <= tol
+        return
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    out = torch.zeros((M, ldo), dtype=torch.float32, device=cuda_device)
+    _lib.check(lib.b200w_skinny_gemm(X.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, K, K, ldo, 1, 1 | tile64, s))
+    torch.cuda.synchronize()
+    assert (out[:, :N] - (ref + bias)).abs().max().item() <= tol
+    out16 = torch.zeros((M, ldo), dtype=torch.bfloat16, device=cuda_device)
+    _lib.check(lib.b200w_skinny_gemm(X.data_ptr(), W.data_ptr(), bias.data_ptr(), out16.data_ptr(), M, N, K, K, K, ldo, 4, 1 | tile64, s))
+    torch.cuda.synchronize()
+    refg = torch.nn.functional.gelu(ref + bias)
+    assert (out16[:, :N].float() - refg).abs().max().item() <= 2e-2 * max(1.0, refg.abs().max().item())
