@@ -19,7 +19,7 @@ void set_last_error(const std::string& s) { t_last_error = s; }
 const char* get_last_error() { return t_last_error.c_str(); }
 
 bool pdl_enabled() {
-  static const bool on = getenv("B200W_PDL") != nullptr;  // measured slightly slower inside the captured decode step: opt-in
+  static const bool on = getenv("B200W_NO_PDL") == nullptr;
   return on;
 }
 

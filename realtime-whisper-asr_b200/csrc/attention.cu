@@ -229,23 +229,28 @@ void enc_attention(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out,
 }
 
 // ------------------------------------------------------------------------------ decoder attention
-static constexpr int DEC_WARPS = 2;
-
-__global__ void __launch_bounds__(DEC_WARPS * 32) dec_attn_kernel(const DecAttnParams p) {
-  extern __shared__ float s_scores[];  // [DEC_WARPS][max_len]
+// One CTA per (query, group of NW heads), one warp per head.  The query's page-table row is staged
+// in shared memory once (all heads of a query share it), so the K and V row loads do not wait on a
+// table load each: a warp keeps one 128-byte K row per lane, then 16 V rows, in flight at a time.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p) {
+  extern __shared__ float s_dyn[];  // [max_len] table (int) | [NW][max_len] scores
   pdl_trigger();
   pdl_wait();
   const int qi = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.y * DEC_WARPS + warp;
-  float* sc = s_scores + warp * p.max_len;
+  const int h = blockIdx.y * NW + warp;
+  int* s_tab = reinterpret_cast<int*>(s_dyn);
+  float* sc = s_dyn + p.max_len + warp * p.max_len;
   const int len = p.kvlen[qi];
   const int tr = p.trow[qi];
-  const int* tab = p.table ? p.table + (long long)tr * p.table_stride : nullptr;
   const long long base = p.kv_base_off ? p.kv_base_off[tr] : 0;
   const bf16* kb = p.kbase + base + h * HD;
   const bf16* vb = p.vbase + base + h * HD;
-
+  {
+    const int* tab = p.table ? p.table + (long long)tr * p.table_stride : nullptr;
+    for (int i = threadIdx.x; i < len; i += NW * 32) s_tab[i] = tab ? tab[i] : i;
+  }
   // q in registers (every lane holds the whole 64-vector, pre-scaled)
   float q[HD];
   {
@@ -262,20 +267,22 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) dec_attn_kernel(const DecAttnP
       }
     }
   }
+  __syncthreads();
   float mx = -INFINITY;
   for (int i = lane; i < len; i += 32) {
-    const long long slot = tab ? tab[i] : i;
-    const bf16* kp = kb + slot * p.kv_row_stride;
+    const bf16* kp = kb + (long long)s_tab[i] * p.kv_row_stride;
+    uint4 kr[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kr[c] = __ldg(reinterpret_cast<const uint4*>(kp) + c);
     float acc = 0.f;
 #pragma unroll
-    for (int c = 0; c < HD; c += 8) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(kp + c));
-      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    for (int c = 0; c < 8; ++c) {
+      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&kr[c]);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float2 f = __bfloat1622float2(u2[t]);
-        acc = fmaf(q[c + 2 * t], f.x, acc);
-        acc = fmaf(q[c + 2 * t + 1], f.y, acc);
+        acc = fmaf(q[8 * c + 2 * t], f.x, acc);
+        acc = fmaf(q[8 * c + 2 * t + 1], f.y, acc);
       }
     }
     sc[i] = acc;
@@ -301,26 +308,31 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) dec_attn_kernel(const DecAttnP
   float2 acc = make_float2(0.f, 0.f);
   const bf16* vl = vb + 2 * lane;
   int i = 0;
-  for (; i + 8 <= len; i += 8) {  // 8 independent 128-byte row reads in flight per warp
-    long long sl[8];
+  for (; i + 16 <= len; i += 16) {  // 16 independent 128-byte row reads in flight per warp
+    __nv_bfloat162 v[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) sl[u] = tab ? tab[i + u] : i + u;
-    __nv_bfloat162 v[8];
+    for (int u = 0; u < 16; ++u)
+      v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)s_tab[i + u] * p.kv_row_stride);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + sl[u] * p.kv_row_stride);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 16; ++u) {
       const float pw = sc[i + u];
       const float2 f = __bfloat1622float2(v[u]);
       acc.x = fmaf(pw, f.x, acc.x);
       acc.y = fmaf(pw, f.y, acc.y);
     }
   }
-  for (; i < len; ++i) {
-    const long long s0 = tab ? tab[i] : i;
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vl + s0 * p.kv_row_stride));
-    acc.x = fmaf(sc[i], f.x, acc.x);
-    acc.y = fmaf(sc[i], f.y, acc.y);
+  {  // ragged tail: still all loads first
+    __nv_bfloat162 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      if (i + u < len) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)s_tab[i + u] * p.kv_row_stride);
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      if (i + u < len) {
+        const float2 f = __bfloat1622float2(v[u]);
+        acc.x = fmaf(sc[i + u], f.x, acc.x);
+        acc.y = fmaf(sc[i + u], f.y, acc.y);
+      }
   }
   bf16* op = p.out + (long long)qi * p.out_stride + h * HD + 2 * lane;
   *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
@@ -328,9 +340,14 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) dec_attn_kernel(const DecAttnP
 
 void dec_attention(const DecAttnParams& p, int n_heads, cudaStream_t stream) {
   if (p.n_queries <= 0) return;
-  B200W_REQUIRE(n_heads % DEC_WARPS == 0, "head count must be even");
-  const size_t smem = (size_t)DEC_WARPS * p.max_len * sizeof(float);
-  launch_pdl(dec_attn_kernel, dim3(p.n_queries, n_heads / DEC_WARPS), dim3(DEC_WARPS * 32), smem, stream, p);
+  B200W_REQUIRE(n_heads % 2 == 0, "head count must be even");
+  if (n_heads % 4 == 0) {
+    const size_t smem = (size_t)(1 + 4) * p.max_len * sizeof(float);
+    launch_pdl(dec_attn_kernel<4>, dim3(p.n_queries, n_heads / 4), dim3(128), smem, stream, p);
+  } else {
+    const size_t smem = (size_t)(1 + 2) * p.max_len * sizeof(float);
+    launch_pdl(dec_attn_kernel<2>, dim3(p.n_queries, n_heads / 2), dim3(64), smem, stream, p);
+  }
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }

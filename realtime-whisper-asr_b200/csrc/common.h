@@ -65,7 +65,7 @@ inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // running.  Contract for every kernel launched through launch_pdl(): pdl_trigger() first, then
 // pdl_wait() in every thread BEFORE the first access to anything another kernel wrote or reads --
 // before any early return, so that grid completion always implies the predecessor's completion.
-// Both are no-ops when the kernel is launched without the attribute (the default; B200W_PDL=1 opts in).
+// Both are no-ops when the kernel is launched without the attribute (B200W_NO_PDL=1).
 bool pdl_enabled();
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -506,14 +506,9 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     RUN(9) {
       OP(9);
       if (sk) {
-        for (int r0 = 0; r0 < n; r0 += 256) {
-          SkinnyDesc g;
-          g.X = h + (long long)r0 * d; g.ldx = d; g.M = std::min(256, n - r0);
-          g.W = L.fc1.w; g.ldw = d; g.N = 4 * d; g.K = d;
-          g.bias = L.fc1.b; g.act = 1;
-          g.out = mlp + (long long)r0 * 4 * d; g.out_fp32 = 0; g.ldo = 4 * d;
-          skinny_gemm(g, s);
-        }
+        // split-K too: 40 weight tiles alone leave most SMs idle; the reduction applies bias + GELU
+        const SplitReduce r = skinny_split(e, h, n, d, L.fc1, 4 * d, 3, s);
+        split_finalize(r.partial, r.n, r.stride, r.bias, n, 4 * d, 1, mlp, 4 * d, nullptr, nullptr, nullptr, 0, s);
       } else {
         linear(h, n, d, L.fc1, 4 * d, mlp, 4 * d, 0, 1, nullptr, 0, 0, s);
       }
