@@ -11,8 +11,15 @@ the "peaked" synthetic model emits ~100-token transcripts ending in EOT, like re
   value     RTFx with the audio already resident in HBM when the timed region starts
   e2e       RTFx through the public host API (numpy in, Python Segment/Word objects out):
             pinned H2D of every chunk and D2H of the results inside the timed region
-  roofline  the dominant kernel (tcgen05 GEMM, 128x256 tiles): algorithmic flops / CUDA-event time
-            of every launch inside the timed region, vs the measured bf16 peak
+  roofline  the kernel with the largest share of the step: the decode-step cross attention
+            (cross_attn_tc_kernel, HBM-bound: every live (stream, head) reads its K and V once per
+            layer per step).  Decode steps are replayed as CUDA graphs in the timed region, where a
+            launch cannot be bracketed by events, so its launches are timed in one extra pass of the
+            same step run eagerly (b200w_op_profile_enable) with CUDA events on the launching stream;
+            achieved = algorithmic bytes / that time, peak = MEASURED_PEAKS.json hbm_gbs
+  roofline_gemm  the encoder's tcgen05 GEMM (128x256 tiles, tensor-bound): algorithmic flops /
+            CUDA-event time of every launch INSIDE the timed region, vs the measured bf16 peak
+  decode_ops  per-op milliseconds of that eager pass (prefill + all decode steps of one step)
   cpu_baseline  the CPU oracle (restatement of the reference's faster-whisper path, fp32) on the
             host cores, on a bounded sample of the same workload (rank 0, N=1 only)
 
@@ -352,16 +359,47 @@ def run_b200(args, rank, world, local):
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
     achieved = (tfl.value / 1e12) / (tms.value / 1e3) if tms.value > 0 else None
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256,4>", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
-                "peak_source": peak_src, "launches_timed": int(tn.value),
-                "kernel_ms_per_step": tms.value / args.steps, "share_of_step": tms.value / dev_ms if dev_ms else None}
+
+    def traffic_of(name):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+
+    roofline_gemm = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256,4,1>", "achieved": achieved,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
+                     "traffic": traffic_of("gemm_traffic.json"), "peak_source": peak_src,
+                     "launches_timed": int(tn.value), "kernel_ms_per_step": tms.value / args.steps,
+                     "share_of_step": tms.value / dev_ms if dev_ms else None,
+                     "timing": "CUDA events around every launch inside the timed region"}
+    # ---- decode ops: one extra pass of the same step, decode steps launched eagerly with events per op
+    _lib.check(lib.b200w_op_profile_enable(1))
+    model.transcribe_batch(None, device_audio=(audio_dev, offsets), **kw)
+    torch.cuda.synchronize()
+    _lib.check(lib.b200w_op_profile_enable(0))
+    ops = {}
+    for op in range(16):
+        nm, ms_, n_, wk_ = C.c_char_p(), C.c_double(), C.c_int64(), C.c_double()
+        _lib.check(lib.b200w_op_profile_read(op, C.byref(nm), C.byref(ms_), C.byref(n_), C.byref(wk_)))
+        if n_.value:
+            ops[nm.value.decode()] = {"ms": ms_.value, "launches": int(n_.value), "work": wk_.value}
+    hbm_peak = peaks.get("hbm_gbs") or 6650.0
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)" if peaks.get("hbm_gbs") else "fallback 6.65 TB/s"
+    x = ops.get("cross_attn")
+    step_ms = dev_ms / args.steps
+    if x and x["ms"] > 0:
+        gbs = x["work"] / 1e9 / (x["ms"] / 1e3)
+        roofline = {"bound": "hbm", "kernel": "cross_attn_tc_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": gbs / hbm_peak, "traffic": traffic_of("cross_tc_traffic.json"), "peak_source": hbm_src,
+                    "launches_timed": x["launches"], "kernel_ms_per_step": x["ms"],
+                    "share_of_step": x["ms"] / step_ms,
+                    "algorithmic_bytes_per_launch": x["work"] / x["launches"],
+                    "timing": "CUDA events around every launch, decode steps run eagerly in one extra pass of the "
+                              "same step (inside the timed region they are CUDA-graph replays)"}
+    else:
+        roofline = dict(roofline_gemm)
+    decode_ops = {k: round(v["ms"], 3) for k, v in ops.items()}
 
     if rank != 0:
         return
@@ -376,6 +414,8 @@ def run_b200(args, rank, world, local):
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": roofline,
+        "roofline_gemm": roofline_gemm,
+        "decode_ops_ms_per_step": decode_ops,
         "tokens_per_step": n_tokens, "words_per_step": n_words,
     }
     if world == 1 and not args.no_side_legs:

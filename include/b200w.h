@@ -41,6 +41,12 @@ uint64_t b200w_launch_count(void);
 /* Development aid: every CTA of later GEMM launches writes 16 int64 timestamps (clock64 / globaltimer)
  * to dev_buf; NULL switches it off. */
 int b200w_gemm_set_trace(void* dev_buf);
+/* Per-op timing of the decoder passes (bench.py's roofline leg for the decode kernels): while enabled,
+ * decode steps are launched eagerly (no CUDA graph) with CUDA events around every op on the launching
+ * stream; totals accumulate per op id until the next enable(1).  read(): op 0..15 -> name, total ms,
+ * launches and algorithmic work (bytes for op 7 = decode cross attention; 0 where not tracked). */
+int b200w_op_profile_enable(int on);
+int b200w_op_profile_read(int op, const char** name, double* total_ms, int64_t* launches, double* work);
 int b200w_gemm_profile_begin(int bn);
 int b200w_gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches);
 

@@ -204,9 +204,14 @@ void linear(const bf16* A, int M, int K, const Lin& l, int N, void* out, int64_t
 // around every op, summed per op type and printed when the decode call returns.
 struct OpTimer {
   bool on = false;
+  bool forced = false;  // b200w_op_profile_enable: decode steps run eagerly so that every op can be bracketed
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
-  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> recs;
+  struct Rec { int id; cudaEvent_t a, b; double work; };
+  std::vector<Rec> recs;
+  double tot_ms[16] = {0}, tot_work[16] = {0};
+  long long tot_n[16] = {0};
+  double next_work = 0;  // algorithmic bytes / flops of the op about to be recorded (set by the caller)
   const char* names[16] = {"embed", "layernorm", "qkv_gemm", "kv_scatter", "self_attn", "out_gemm", "cq_gemm",
                            "cross_attn", "cout_gemm", "fc1_gemm", "fc2_gemm", "logits_gemm", "sample", "fork",
                            "final_ln", "other"};
@@ -218,20 +223,25 @@ struct OpTimer {
     }
     return pool[used++];
   }
-  void report(const char* tag) {
+  void collect(const char* tag) {
     if (!on || recs.empty()) return;
     double tot[16] = {0};
     int cnt[16] = {0};
     for (auto& r : recs) {
       float ms = 0;
-      cudaEventSynchronize(r.second.second);
-      cudaEventElapsedTime(&ms, r.second.first, r.second.second);
-      tot[r.first] += ms;
-      cnt[r.first]++;
+      cudaEventSynchronize(r.b);
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      tot[r.id] += ms;
+      cnt[r.id]++;
+      tot_ms[r.id] += ms;
+      tot_work[r.id] += r.work;
+      tot_n[r.id]++;
     }
-    fprintf(stderr, "[b200w op profile] %s\n", tag);
-    for (int i = 0; i < 16; ++i)
-      if (cnt[i]) fprintf(stderr, "   %-12s n=%6d total %9.3f ms  avg %8.2f us\n", names[i], cnt[i], tot[i], 1000.0 * tot[i] / cnt[i]);
+    if (getenv("B200W_DECODE_PROFILE")) {
+      fprintf(stderr, "[b200w op profile] %s\n", tag);
+      for (int i = 0; i < 16; ++i)
+        if (cnt[i]) fprintf(stderr, "   %-12s n=%6d total %9.3f ms  avg %8.2f us\n", names[i], cnt[i], tot[i], 1000.0 * tot[i] / cnt[i]);
+    }
     recs.clear();
     used = 0;
   }
@@ -241,11 +251,12 @@ struct OpScope {
   int id;
   cudaStream_t s;
   cudaEvent_t a = nullptr;
+  double work = 0;
   OpScope(int id_, cudaStream_t s_) : id(id_), s(s_) {
-    if (g_optimer.on) { a = g_optimer.ev(); cudaEventRecord(a, s); }
+    if (g_optimer.on) { a = g_optimer.ev(); work = g_optimer.next_work; g_optimer.next_work = 0; cudaEventRecord(a, s); }
   }
   ~OpScope() {
-    if (a) { cudaEvent_t b = g_optimer.ev(); cudaEventRecord(b, s); g_optimer.recs.push_back({id, {a, b}}); }
+    if (a) { cudaEvent_t b = g_optimer.ev(); cudaEventRecord(b, s); g_optimer.recs.push_back({id, a, b, work}); }
   }
 };
 #define OP(id) OpScope _op_scope_##id(id, s)
@@ -325,6 +336,7 @@ struct PassMeta {  // device pointers into e->meta for one forward pass of n tok
   int *tok, *pos, *slot, *trow, *kvlen, *stream, *parent;
   int *g_start, *g_count;  // cross-attention groups: runs of <= 8 rows of one stream (live groups first)
   int* n_live = nullptr;   // device: number of groups with at least one live row
+  int n_live_host = 0;
   int n_groups = 0, max_group = 1;
   int4* state;
 };
@@ -407,6 +419,7 @@ PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) 
   m.g_count = dp + 7 * n + ng;
   m.n_groups = ng;
   m.n_live = dp + 7 * n + 2 * ng;
+  m.n_live_host = n_live;
   m.max_group = max_cap;  // capacity, not the live count: keeps the launch shape fixed
   m.state = reinterpret_cast<int4*>(reinterpret_cast<char*>(dp) + st_off);
   return m;
@@ -493,8 +506,12 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     }
     static const bool use_tc = getenv("B200W_NO_CROSS_TC") == nullptr;
     RUN(7) {
-      OP(7);
-      if (use_tc && !c.head_export && m.max_group <= CROSS_GROUP && m.n_groups <= 64)
+      const bool tc = use_tc && !c.head_export && m.max_group <= CROSS_GROUP && m.n_groups <= 64;
+      // decode steps (tensor-core kernel) are op 7, with their algorithmic bytes: K and V of every live
+      // (group, head), read once; prompt / alignment passes are timed under "other"
+      if (tc) g_optimer.next_work = (double)m.n_live_host * e->H * 2.0 * e->Tenc * HEAD_DIM * 2.0;
+      OpScope _op_scope_x(tc ? 7 : 15, s);
+      if (tc)
         cross_attention_tc(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, d, m.stream, m.g_start, m.g_count,
                            m.n_live, m.n_groups, attn, d, 0.125f, e->x_tc.p, s);
       else
@@ -813,7 +830,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
   }
 
   const bool timing = getenv("B200W_DECODE_TIMING") != nullptr;
-  g_optimer.on = getenv("B200W_DECODE_PROFILE") != nullptr && !e->use_graphs;
+  g_optimer.on = g_optimer.forced || (getenv("B200W_DECODE_PROFILE") != nullptr && !e->use_graphs);
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration<double, std::milli>(now() - t0).count();
@@ -982,7 +999,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
       e->step_graphs.clear();
       e->h_meta.grew = e->h_out.grew = false;
     }
-    if (e->use_graphs && step >= 2) {
+    if (e->use_graphs && step >= 2 && !g_optimer.on) {
       for (auto& g : e->step_graphs)
         if (g.ckv == ckv && g.B == B && g.K == K && g.parity == cur && g.opts_hash == opts_hash) exec = g.exec;
       if (!exec) {
@@ -1068,7 +1085,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     }
     t_book += ms_since(t_s2);
   }
-  g_optimer.report("decode (prefill + steps)");
+  g_optimer.collect("decode (prefill + steps)");
   if (timing)
     fprintf(stderr, "[b200w_decode] B=%d K=%d steps=%d prefill+first=%.2f ms, per step: fill %.3f ms, launch+gpu %.3f ms, "
             "bookkeeping %.3f ms, total %.1f ms\n", B, K, n_steps, t_prefill, t_fill / std::max(n_steps, 1),
@@ -1263,3 +1280,19 @@ int b200w_align(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t*
 }
 
 }  // extern "C"
+
+extern "C" int b200w_op_profile_enable(int on) {
+  g_optimer.forced = on != 0;
+  if (on) {
+    for (int i = 0; i < 16; ++i) { g_optimer.tot_ms[i] = 0; g_optimer.tot_work[i] = 0; g_optimer.tot_n[i] = 0; }
+  }
+  return 0;
+}
+extern "C" int b200w_op_profile_read(int op, const char** name, double* total_ms, int64_t* launches, double* work) {
+  if (op < 0 || op >= 16) return -1;
+  if (name) *name = g_optimer.names[op];
+  if (total_ms) *total_ms = g_optimer.tot_ms[op];
+  if (launches) *launches = g_optimer.tot_n[op];
+  if (work) *work = g_optimer.tot_work[op];
+  return 0;
+}
