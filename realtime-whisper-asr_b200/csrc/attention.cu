@@ -831,7 +831,8 @@ static constexpr int XT_RING = 5;    // 16 KB slots; two CTAs share an SM and co
 static constexpr int XT_MAX_TILES = 12;  // keys <= 1536
 static constexpr int XT_P_BYTES = XT_MAX_TILES * 2 * 1024;
 static constexpr int XT_Q_BYTES = 2048;
-static constexpr int XT_SMEM = XT_P_BYTES + XT_Q_BYTES + XT_RING * TILE_BYTES + 512 + 1024;
+static constexpr int XT_N_BARS = 2 * XT_RING + 2 * XT_MAX_TILES + 4;
+static constexpr int XT_SMEM = XT_P_BYTES + 2 * XT_Q_BYTES + XT_RING * TILE_BYTES + XT_N_BARS * 8 + 256 + 16 + 1024;
 static constexpr int XT_MAX_PIECES = 6;
 static constexpr int XT_CTAS_PER_SM = 2;
 static constexpr int XT_PART_FLOATS = 8 * 64 + 16;  // O[8][64], m[8], l[8]
@@ -882,82 +883,52 @@ __device__ __forceinline__ bool xt_unit(int u, int n_items, int n_tiles, XtUnit&
   return true;
 }
 
-// Softmax of one unit for the 128 softmax threads.  Thread = key row of every tile; NQ query columns
-// per tile are read from TMEM four tiles at a time (twice: once for the max, once for the
-// exponentials) to stay inside 168 registers.  Leaves P (bf16, K-major operand tiles, row = query,
-// column = key) in shared memory, per-warp maxima in s_red[0..32) and per-warp sums in s_red[32..64).
+// Softmax of one unit, spread over the two streaming phases so that it hides behind the loads
+// (thread = key row of every tile; NQ live query columns per tile):
+//   pass 1, while the K tiles stream in: as soon as tile j's scores are in TMEM, fold them into the
+//           running per-query maximum;
+//   pass 2, while the V tiles stream in: P_j = exp2((s - max) * c) as bf16 into tile j's K-major operand
+//           buffer (row = query, column = key), released to the MMA issuer tile by tile.
 // Rows of dead queries (q >= NQ) keep stale values: they only feed output rows nobody reads.
 template <int NQ>
-__device__ __forceinline__ void xt_softmax(const int len, const float scale_log2e, uint32_t tS, uint8_t* sP,
-                                           float* s_red, int t0, int nt) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int key0 = t0 * 128 + tid;
-  float mx[NQ];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) mx[q] = -INFINITY;
+__device__ __forceinline__ void xt_pass1(int len, uint32_t tS, uint32_t bar_s0, uint32_t parity, int t0, int nt,
+                                         float (&mx)[8]) {
+  const int key0 = t0 * 128 + (int)threadIdx.x;
 #pragma unroll 1
-  for (int jc = 0; jc < nt; jc += 4) {
-    uint32_t sc[4][8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (jc + j < nt) tmem_ld8(tS + 16 * (jc + j), sc[j]);
+  for (int j = 0; j < nt; ++j) {
+    mbar_wait(bar_s0 + 8 * j, parity);
+    tc_fence_after();
+    uint32_t sc[8];
+    tmem_ld8(tS + 16 * j, sc);
     tmem_ld_wait();
+    if (key0 + j * 128 < len) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (jc + j < nt && key0 + (jc + j) * 128 < len) {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) mx[q] = fmaxf(mx[q], __uint_as_float(sc[j][q]));
-      }
+      for (int q = 0; q < NQ; ++q) mx[q] = fmaxf(mx[q], __uint_as_float(sc[q]));
+    }
   }
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    for (int o = 16; o > 0; o >>= 1) mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
-  }
-  if (lane < 8) {
-    float v = mx[0];
-#pragma unroll
-    for (int q = 1; q < NQ; ++q) v = lane == q ? mx[q] : v;
-    s_red[warp * 8 + lane] = v;
-  }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  float sum[NQ];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const float m = fmaxf(fmaxf(s_red[q], s_red[8 + q]), fmaxf(s_red[16 + q], s_red[24 + q]));
-    mx[q] = m * scale_log2e;
-    sum[q] = 0.f;
-  }
+}
+template <int NQ>
+__device__ __forceinline__ void xt_pass2(int len, float scale_log2e, uint32_t tS, uint8_t* sP, uint32_t bar_p0, int t0,
+                                         int nt, const float (&mxs)[8], float (&sum)[8]) {
+  const int tid = threadIdx.x;
+  const int key0 = t0 * 128 + tid;
   const int kc = tid & 63, half = tid >> 6;
   uint8_t* prow = sP + half * 1024 + (kc & 7) * 2;
 #pragma unroll 1
-  for (int jc = 0; jc < nt; jc += 4) {
-    uint32_t sc[4][8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (jc + j < nt) tmem_ld8(tS + 16 * (jc + j), sc[j]);
+  for (int j = 0; j < nt; ++j) {
+    uint32_t sc[8];
+    tmem_ld8(tS + 16 * j, sc);
     tmem_ld_wait();
+    const bool valid = key0 + j * 128 < len;
+    uint8_t* pt = prow + j * 2048;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (jc + j < nt) {
-        const bool valid = key0 + (jc + j) * 128 < len;
-        uint8_t* pt = prow + (jc + j) * 2048;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const float e = valid ? ex2_approx(fmaf(__uint_as_float(sc[j][q]), scale_log2e, -mx[q])) : 0.f;
-          sum[q] += e;
-          *reinterpret_cast<bf16*>(pt + q * 128 + (((kc >> 3) ^ q) << 4)) = __float2bfloat16(e);
-        }
-      }
-  }
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    for (int o = 16; o > 0; o >>= 1) sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
-  }
-  if (lane < 8) {
-    float v = sum[0];
-#pragma unroll
-    for (int q = 1; q < NQ; ++q) v = lane == q ? sum[q] : v;
-    s_red[32 + warp * 8 + lane] = v;
+    for (int q = 0; q < NQ; ++q) {
+      const float e = valid ? ex2_approx(fmaf(__uint_as_float(sc[q]), scale_log2e, -mxs[q])) : 0.f;
+      sum[q] += e;
+      *reinterpret_cast<bf16*>(pt + q * 128 + (((kc >> 3) ^ q) << 4)) = __float2bfloat16(e);
+    }
+    fence_proxy_async_smem();
+    mbar_arrive(bar_p0 + 8 * j);
   }
 }
 
@@ -967,23 +938,24 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sP = smem;
-  uint8_t* sQ = sP + XT_P_BYTES;
-  uint8_t* ring = sQ + XT_Q_BYTES;
+  uint8_t* sQ = sP + XT_P_BYTES;            // two [16][64] Q tiles (double-buffered across units)
+  uint8_t* ring = sQ + 2 * XT_Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + XT_RING * TILE_BYTES);
-  float* s_red = reinterpret_cast<float*>(bars + 2 * XT_RING + 4);  // [2][4][8]
+  float* s_red = reinterpret_cast<float*>(bars + XT_N_BARS);  // [2][4][8]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_red + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + XT_RING);
-  const uint32_t bar_q = smem_u32(bars + 2 * XT_RING), bar_s = bar_q + 8, bar_p = bar_q + 16, bar_o = bar_q + 24;
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * XT_RING;
+  const uint32_t bar_s0 = empty0 + 8 * XT_RING;           // [12] scores of tile j are in TMEM
+  const uint32_t bar_p0 = bar_s0 + 8 * XT_MAX_TILES;      // [12] P of tile j is in shared memory
+  const uint32_t bar_q0 = bar_p0 + 8 * XT_MAX_TILES;      // [2]  Q buffer b is staged
+  const uint32_t bar_sfree = bar_q0 + 16, bar_o = bar_sfree + 8;
   pdl_trigger();
   if (tid == 0) {
-    for (int i = 0; i < XT_RING; ++i) {
-      mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, 1);
-    }
-    mbar_init(bar_q, 128);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    for (int i = 0; i < 2 * XT_RING + XT_MAX_TILES; ++i) mbar_init(full0 + 8 * i, 1);   // ring + bar_s
+    for (int i = 0; i < XT_MAX_TILES; ++i) mbar_init(bar_p0 + 8 * i, 128);
+    mbar_init(bar_q0, 31);
+    mbar_init(bar_q0 + 8, 31);
+    mbar_init(bar_sfree, 128);
     mbar_init(bar_o, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmKV);
@@ -1017,17 +989,45 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
             if (++slot == XT_RING) { slot = 0; phase ^= 1; }
           }
       }
+    } else {  // ---------------- lanes 1..31: stage the Q tile of unit `it` one unit ahead of its use
+      pdl_wait();
+      for (int it = 0; xt_unit(it, n_items, n_tiles, un); ++it) {
+        const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
+        const int q0 = p.g_start[g], nq = p.g_count[g];
+        uint4 u[5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {  // 128 16-byte pieces over 31 lanes
+          const int i = (lane - 1) + 31 * r;
+          const int qr = i >> 3, ch = i & 7;
+          u[r] = make_uint4(0u, 0u, 0u, 0u);
+          if (i < 128 && qr < nq)
+            u[r] = *reinterpret_cast<const uint4*>(p.q + (long long)(q0 + qr) * p.q_stride + h * HD + 8 * ch);
+        }
+        // buffer it&1 was last read by the QK MMAs of unit it-2: its last score barrier tells when they are done
+        if (it >= 2) mbar_wait(bar_s0 + 8 * (n_tiles - 1), (uint32_t)(it & 1));  // unit it-2 is a whole item
+        uint8_t* dst = sQ + (it & 1) * XT_Q_BYTES;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const int i = (lane - 1) + 31 * r;
+          const int qr = i >> 3, ch = i & 7;
+          if (i < 128) *reinterpret_cast<uint4*>(dst + qr * 128 + ((ch ^ (qr & 7)) << 4)) = u[r];
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_q0 + 8 * (it & 1));
+      }
     }
   } else if (warp == 5) {
     if (lane == 0) {  // ---------------- MMA issuer
       constexpr uint32_t idescS = make_idesc_bf16(128, 16, 0, 0);  // K (K-major) x Q (K-major)
       constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);  // P (K-major) x V (MN-major)
       uint32_t slot = 0, phase = 0;
-      const uint64_t qd = make_sw128_desc(smem_u32(sQ));
       for (int it = 0; xt_unit(it, n_items, n_tiles, un); ++it) {
         const int nt = un.t1 - un.t0;
-        mbar_wait(bar_q, it & 1);
+        const uint32_t par = it & 1;
+        mbar_wait(bar_q0 + 8 * par, (uint32_t)((it >> 1) & 1));
+        if (it > 0) mbar_wait(bar_sfree, par ^ 1);  // the softmax of the unit before is done with the scores
         tc_fence_after();
+        const uint64_t qd = make_sw128_desc(smem_u32(sQ + par * XT_Q_BYTES));
         for (int j = 0; j < nt; ++j) {
           mbar_wait(full0 + 8 * slot, phase);
           tc_fence_after();
@@ -1035,12 +1035,11 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_S + 16 * j, kd + 2 * k, qd + 2 * k, idescS, k != 0);
           tc_commit(empty0 + 8 * slot);
+          tc_commit(bar_s0 + 8 * j);
           if (++slot == XT_RING) { slot = 0; phase ^= 1; }
         }
-        tc_commit(bar_s);
-        mbar_wait(bar_p, it & 1);
-        tc_fence_after();
         for (int j = 0; j < nt; ++j) {
+          mbar_wait(bar_p0 + 8 * j, par);
           mbar_wait(full0 + 8 * slot, phase);
           tc_fence_after();
           const uint64_t vd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
@@ -1055,36 +1054,56 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
         tc_commit(bar_o);
       }
     }
-  } else {  // ---------------- warps 0..3: Q staging, softmax (thread = key row of every tile), output
+  } else {  // ---------------- warps 0..3: softmax (thread = key row of every tile) and output
     pdl_wait();
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
     for (int it = 0; xt_unit(it, n_items, n_tiles, un); ++it) {
       const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
       const int q0 = p.g_start[g], nq = p.g_count[g];
       const int nt = un.t1 - un.t0;
-      {  // Q -> swizzled K-major [16][64] tile (rows >= nq zero)
-        const int qr = tid >> 3, ch = tid & 7;
-        uint4 u = make_uint4(0u, 0u, 0u, 0u);
-        if (qr < nq) u = *reinterpret_cast<const uint4*>(p.q + (long long)(q0 + qr) * p.q_stride + h * HD + 8 * ch);
-        *reinterpret_cast<uint4*>(sQ + qr * 128 + ((ch ^ (qr & 7)) << 4)) = u;
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(bar_q);
+      const uint32_t par = it & 1;
       if (tid == 0) XT_TRACE(0);
-      mbar_wait(bar_s, it & 1);
-      tc_fence_after();
+      float mx[8], sum[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { mx[q] = -INFINITY; sum[q] = 0.f; }
+      if (nq <= 1) xt_pass1<1>(p.len, tmem_S + lane_sel, bar_s0, par, un.t0, nt, mx);
+      else if (nq <= 2) xt_pass1<2>(p.len, tmem_S + lane_sel, bar_s0, par, un.t0, nt, mx);
+      else if (nq <= 5) xt_pass1<5>(p.len, tmem_S + lane_sel, bar_s0, par, un.t0, nt, mx);
+      else xt_pass1<8>(p.len, tmem_S + lane_sel, bar_s0, par, un.t0, nt, mx);
       if (tid == 0) XT_TRACE(1);
-      // softmax over the unit's keys, specialised on the number of live queries (branch-free inner loops)
-      if (nq <= 1) xt_softmax<1>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, s_red, un.t0, nt);
-      else if (nq <= 2) xt_softmax<2>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, s_red, un.t0, nt);
-      else if (nq <= 5) xt_softmax<5>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, s_red, un.t0, nt);
-      else xt_softmax<8>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, s_red, un.t0, nt);
-      if (tid == 0) XT_TRACE(7);
-      fence_proxy_async_smem();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        for (int o = 16; o > 0; o >>= 1) mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
+      }
+      if (lane < 8) {
+        float v = mx[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) v = lane == q ? mx[q] : v;
+        s_red[warp * 8 + lane] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        mx[q] = fmaxf(fmaxf(s_red[q], s_red[8 + q]), fmaxf(s_red[16 + q], s_red[24 + q])) * p.scale_log2e;
+      if (nq <= 1) xt_pass2<1>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, bar_p0, un.t0, nt, mx, sum);
+      else if (nq <= 2) xt_pass2<2>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, bar_p0, un.t0, nt, mx, sum);
+      else if (nq <= 5) xt_pass2<5>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, bar_p0, un.t0, nt, mx, sum);
+      else xt_pass2<8>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, bar_p0, un.t0, nt, mx, sum);
       tc_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive(bar_sfree);  // scores consumed: the next unit's QK MMAs may overwrite them
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        for (int o = 16; o > 0; o >>= 1) sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
+      }
+      if (lane < 8) {
+        float v = sum[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) v = lane == q ? sum[q] : v;
+        s_red[32 + warp * 8 + lane] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // partial sums visible to warp 0
       if (tid == 0) XT_TRACE(2);
-      mbar_wait(bar_o, it & 1);
+      mbar_wait(bar_o, par);
       tc_fence_after();
       if (tid == 0) XT_TRACE(3);
       if (warp == 0) {
@@ -1169,7 +1188,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
         }
       }
       tc_fence_before();
-      // s_red / sQ / sP are rewritten by the next unit: everyone must be past their reads first
+      // s_red / sP are rewritten by the next unit: everyone must be past their reads first
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (tid == 0) XT_TRACE(4);
     }

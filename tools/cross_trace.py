@@ -33,8 +33,7 @@ for it in range(6):
         continue
     x = t[m, it]
     a, b, c, d = x[:, 1] - x[:, 0], x[:, 2] - x[:, 1], x[:, 3] - x[:, 2], x[:, 4] - x[:, 3]
-    line = f"item {it}: ctas {m.sum():3d}  A(wait K + QK) {np.median(a):7.0f}  B(softmax) {np.median(b):7.0f}  C(wait V + PV) {np.median(c):7.0f}  D(out) {np.median(d):6.0f}"
-    line += f" | B: tmem_ld {np.median(x[:, 5] - x[:, 1]):5.0f} max {np.median(x[:, 6] - x[:, 5]):5.0f} exp+sum {np.median(x[:, 7] - x[:, 6]):5.0f} fence {np.median(x[:, 2] - x[:, 7]):5.0f}"
+    line = f"item {it}: ctas {m.sum():3d}  pass1(K stream) {np.median(a):7.0f}  max+pass2 {np.median(b):7.0f}  wait PV done {np.median(c):7.0f}  out {np.median(d):6.0f}"
     if it > 0:
         m2 = m & ok[:, it - 1]
         line += f"   period {np.median(t[m2, it, 0] - t[m2, it - 1, 0]):7.0f} cycles"
