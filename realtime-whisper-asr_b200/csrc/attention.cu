@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnPara
   pdl_wait();
   const int q0 = p.g_start[g], nq = p.g_count[g];
   if (nq == 0) return;
+  if (p.export_only && p.head_export[h] < 0) return;
   const long long base = p.kv_base_off[p.stream[q0]];
   const bf16* kb = p.kbase + base + h * p.head_stride;
   const bf16* vb = p.vbase + base + h * p.head_stride;

@@ -54,6 +54,7 @@ struct CrossAttnParams {
   float* probs_out = nullptr;              // optional [n_export][n_queries][probs_stride]
   const int* head_export = nullptr;        // [n_heads] -> export index or -1
   int probs_stride = 0;
+  int export_only = 0;  // 1: only heads with head_export[h] >= 0 are computed (the others were done elsewhere)
 };
 // max_group: upper bound on g_count (selects the specialisation of the streaming kernel)
 // split_scratch (optional, cross_attention_scratch_bytes(64, n_heads) bytes): enables the split-KV path

@@ -506,16 +506,25 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     }
     static const bool use_tc = getenv("B200W_NO_CROSS_TC") == nullptr;
     RUN(7) {
-      const bool tc = use_tc && !c.head_export && m.max_group <= CROSS_GROUP && m.n_groups <= 64;
-      // decode steps (tensor-core kernel) are op 7, with their algorithmic bytes: K and V of every live
-      // (group, head), read once; prompt / alignment passes are timed under "other"
-      if (tc) g_optimer.next_work = (double)m.n_live_host * e->H * 2.0 * e->Tenc * HEAD_DIM * 2.0;
-      OpScope _op_scope_x(tc ? 7 : 15, s);
-      if (tc)
+      // Tensor-core kernel for every pass whose groups fit it (decode steps, prompts, alignment).  Heads whose
+      // probabilities are exported (alignment pass) are then recomputed by the CUDA-core kernel, which writes
+      // the probabilities and overwrites those heads' outputs (export_only skips every other head).
+      const bool step_tc = use_tc && !c.head_export && m.max_group <= CROSS_GROUP && m.n_groups <= 64;
+      const bool tc = use_tc && m.max_group <= CROSS_GROUP;
+      // decode steps are op 7, with their algorithmic bytes: K and V of every live (group, head), read once;
+      // prompt / alignment passes are timed under "other"
+      if (step_tc) g_optimer.next_work = (double)m.n_live_host * e->H * 2.0 * e->Tenc * HEAD_DIM * 2.0;
+      OpScope _op_scope_x(step_tc ? 7 : 15, s);
+      if (tc) {
         cross_attention_tc(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, d, m.stream, m.g_start, m.g_count,
                            m.n_live, m.n_groups, attn, d, 0.125f, e->x_tc.p, s);
-      else
+        if (c.head_export) {
+          c.export_only = 1;
+          cross_attention(c, m.n_groups, e->H, m.max_group, s, nullptr);
+        }
+      } else {
         cross_attention(c, m.n_groups, e->H, m.max_group, s, e->x_split.as<float>());
+      }
     }
     RUN(8) { OP(8); pend = residual_linear(e, attn, n, d, L.cout, x, s); }
     // MLP
