@@ -302,17 +302,18 @@ __device__ __forceinline__ bool token_masked(int v, const SampleParams& p, const
   return token_masked_m(v, mask[v], p, st);
 }
 
-// One CTA (1024 threads) per row: masked log-softmax with Whisper's timestamp rules, then top-k.
+// One CTA (512 threads) per row: masked log-softmax with Whisper's timestamp rules, then top-k.
 // Pass 1 applies the rules once and writes the masked logits back (-inf where barred), so the later
 // passes are plain streaming reads of an L2-resident row.
-static constexpr int SAMPLE_THREADS = 1024;
+static constexpr int SAMPLE_THREADS = 512;
+static constexpr int SAMPLE_WARPS = SAMPLE_THREADS / 32;
 
 __device__ __forceinline__ float block_max_1024(float v, float* s) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   __syncthreads();
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
   __syncthreads();
-  float r = s[threadIdx.x & 31];
+  float r = (threadIdx.x & 31) < SAMPLE_WARPS ? s[threadIdx.x & 31] : -INFINITY;
   for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
   return r;
 }
@@ -321,7 +322,7 @@ __device__ __forceinline__ float block_sum_1024(float v, float* s) {
   __syncthreads();
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
   __syncthreads();
-  float r = s[threadIdx.x & 31];
+  float r = (threadIdx.x & 31) < SAMPLE_WARPS ? s[threadIdx.x & 31] : 0.f;
   for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
   return r;
 }
@@ -397,21 +398,30 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
     }
   }
 
-  // per-thread top-k (k <= MAX_TOPK), kept sorted descending; ties -> lower token id first
+  // per-thread top-k (k <= MAX_TOPK), kept sorted descending; ties -> lower token id first.
+  // The lists live in registers: an insert is a fully unrolled shift chain (no dynamic indexing, which
+  // would put the arrays in local memory); after the first few elements almost nothing passes `thresh`.
   float bv[MAX_TOPK];
   int bi[MAX_TOPK];
 #pragma unroll
   for (int j = 0; j < MAX_TOPK; ++j) { bv[j] = -INFINITY; bi[j] = 0x7fffffff; }
   const int k = p.k;
-  float thresh = -INFINITY;  // == bv[k-1], kept in a register
+  float thresh = -INFINITY;  // == bv[k-1]
   auto consider = [&](float xr, int v) {
     const float x = xr - lse;
     if (v >= v_lo && x > thresh) {
-      int j = k - 1;
-      while (j > 0 && x > bv[j - 1]) { bv[j] = bv[j - 1]; bi[j] = bi[j - 1]; --j; }
-      bv[j] = x;
-      bi[j] = v;
-      thresh = bv[k - 1];
+      // tokens are visited in increasing id order per thread, so a strict '>' keeps the lower id first on ties
+#pragma unroll
+      for (int j = MAX_TOPK - 1; j > 0; --j) {
+        const bool shift = j < k && x > bv[j - 1];      // element j-1 moves down to j
+        const bool here = j < k && !shift && x > bv[j];  // x lands at j
+        if (shift) { bv[j] = bv[j - 1]; bi[j] = bi[j - 1]; }
+        else if (here) { bv[j] = x; bi[j] = v; }
+      }
+      if (x > bv[0]) { bv[0] = x; bi[0] = v; }
+#pragma unroll
+      for (int j = 0; j < MAX_TOPK; ++j)
+        if (j == k - 1) thresh = bv[j];
     }
   };
   for (int i = tid; i < nv4; i += SAMPLE_THREADS) {
@@ -425,8 +435,11 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
   int head = 0;
   for (int r = 0; r < k; ++r) {
     // block argmax over every thread's current head; ties -> lower id
-    float cv = head < k ? bv[head] : -INFINITY;
-    int ci = head < k ? bi[head] : 0x7fffffff;
+    float cv = -INFINITY;
+    int ci = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < MAX_TOPK; ++j)
+      if (j == head && j < k) { cv = bv[j]; ci = bi[j]; }
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
       const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
@@ -435,8 +448,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
     __syncthreads();
     if ((tid & 31) == 0) { s_cv[tid >> 5] = cv; s_ci[tid >> 5] = ci; }
     __syncthreads();
-    cv = s_cv[tid & 31];
-    ci = s_ci[tid & 31];
+    cv = (tid & 31) < SAMPLE_WARPS ? s_cv[tid & 31] : -INFINITY;
+    ci = (tid & 31) < SAMPLE_WARPS ? s_ci[tid & 31] : 0x7fffffff;
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
       const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
@@ -446,7 +459,11 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
       p.out_ids[row * k + r] = ci;
       p.out_logprobs[row * k + r] = cv;
     }
-    if (head < k && bi[head] == ci && ci != 0x7fffffff) ++head;
+    int my = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < MAX_TOPK; ++j)
+      if (j == head && j < k) my = bi[j];
+    if (my == ci && ci != 0x7fffffff) ++head;
   }
 }
 
