@@ -269,24 +269,33 @@ __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p
   }
   __syncthreads();
   float mx = -INFINITY;
-  for (int i = lane; i < len; i += 32) {
-    const bf16* kp = kb + (long long)s_tab[i] * p.kv_row_stride;
-    uint4 kr[8];
+  for (int i0 = lane; i0 < len; i0 += 64) {  // two keys per lane per round: 16 independent 16-byte loads in flight
+    const int i1 = i0 + 32;
+    const bool has1 = i1 < len;
+    const bf16* kp0 = kb + (long long)s_tab[i0] * p.kv_row_stride;
+    const bf16* kp1 = kb + (long long)s_tab[has1 ? i1 : i0] * p.kv_row_stride;
+    uint4 kr0[8], kr1[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) kr[c] = __ldg(reinterpret_cast<const uint4*>(kp) + c);
-    float acc = 0.f;
+    for (int c = 0; c < 8; ++c) kr0[c] = __ldg(reinterpret_cast<const uint4*>(kp0) + c);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kr1[c] = __ldg(reinterpret_cast<const uint4*>(kp1) + c);
+    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&kr[c]);
+      const __nv_bfloat162* u0 = reinterpret_cast<const __nv_bfloat162*>(&kr0[c]);
+      const __nv_bfloat162* u1 = reinterpret_cast<const __nv_bfloat162*>(&kr1[c]);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float2 f = __bfloat1622float2(u2[t]);
-        acc = fmaf(q[8 * c + 2 * t], f.x, acc);
-        acc = fmaf(q[8 * c + 2 * t + 1], f.y, acc);
+        const float2 f0 = __bfloat1622float2(u0[t]), f1 = __bfloat1622float2(u1[t]);
+        a0 = fmaf(q[8 * c + 2 * t], f0.x, a0);
+        a0 = fmaf(q[8 * c + 2 * t + 1], f0.y, a0);
+        a1 = fmaf(q[8 * c + 2 * t], f1.x, a1);
+        a1 = fmaf(q[8 * c + 2 * t + 1], f1.y, a1);
       }
     }
-    sc[i] = acc;
-    mx = fmaxf(mx, acc);
+    sc[i0] = a0;
+    mx = fmaxf(mx, a0);
+    if (has1) { sc[i1] = a1; mx = fmaxf(mx, a1); }
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.f;
@@ -308,13 +317,13 @@ __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p
   float2 acc = make_float2(0.f, 0.f);
   const bf16* vl = vb + 2 * lane;
   int i = 0;
-  for (; i + 16 <= len; i += 16) {  // 16 independent 128-byte row reads in flight per warp
-    __nv_bfloat162 v[16];
+  for (; i + 32 <= len; i += 32) {  // 32 independent 128-byte row reads in flight per warp
+    __nv_bfloat162 v[32];
 #pragma unroll
-    for (int u = 0; u < 16; ++u)
+    for (int u = 0; u < 32; ++u)
       v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)s_tab[i + u] * p.kv_row_stride);
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
+    for (int u = 0; u < 32; ++u) {
       const float pw = sc[i + u];
       const float2 f = __bfloat1622float2(v[u]);
       acc.x = fmaf(pw, f.x, acc.x);
@@ -322,12 +331,12 @@ __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p
     }
   }
   {  // ragged tail: still all loads first
-    __nv_bfloat162 v[16];
+    __nv_bfloat162 v[32];
 #pragma unroll
-    for (int u = 0; u < 16; ++u)
+    for (int u = 0; u < 32; ++u)
       if (i + u < len) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)s_tab[i + u] * p.kv_row_stride);
 #pragma unroll
-    for (int u = 0; u < 16; ++u)
+    for (int u = 0; u < 32; ++u)
       if (i + u < len) {
         const float2 f = __bfloat1622float2(v[u]);
         acc.x = fmaf(sc[i + u], f.x, acc.x);
