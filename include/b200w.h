@@ -96,6 +96,18 @@ int b200w_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev,
 int b200w_skinny_gemm(const void* X_dev, const void* W_dev, const float* bias_dev, void* out_dev, int M, int N,
                       int K, int64_t ldx, int64_t ldw, int64_t ldo, int flags, int splits, void* stream);
 
+/* Decode-step cross attention on tcgen05 (csrc/attention.cu, cross_attn_tc_kernel): groups of <= 8 consecutive
+ * query rows of one stream share one pass over that stream's keys / values.
+ *   cross_kv_dev  bf16 [n_streams][n_layers][k|v][n_heads][len][64]       q_dev  bf16 [rows][n_heads*64]
+ *   stream_dev    int32 [rows] stream of each row       g_start_dev / g_count_dev  int32 [n_groups]
+ *   n_live_dev    int32 [1]: groups [0, n_live) are processed             out_dev bf16 [rows][n_heads*64]
+ *   scratch_dev   b200w_cross_attention_tc_scratch_bytes() bytes, zeroed once by the caller */
+int64_t b200w_cross_attention_tc_scratch_bytes(void);
+int b200w_cross_attention_tc(const void* cross_kv_dev, int n_streams, int n_layers, int layer, int n_heads, int len,
+                             const void* q_dev, const int32_t* stream_dev, const int32_t* g_start_dev,
+                             const int32_t* g_count_dev, const int32_t* n_live_dev, int n_groups, void* out_dev,
+                             float scale, void* scratch_dev, void* stream);
+
 /* conv1d (kernel 3, padding 1, stride 1 or 2) as implicit GEMM over time-major activations:
  * x bf16 [B][T][C] -> GELU(conv(x) + bias) (+ addend fp32 [T_out][N], e.g. positions) ->
  * out [B][T_out][N] bf16 or fp32.  w bf16 [N][3*C] tap-major.  C % 64 == 0. */

@@ -150,6 +150,20 @@ int b200w_skinny_gemm(const void* X_dev, const void* W_dev, const float* bias_de
   B200W_API_END
 }
 
+int64_t b200w_cross_attention_tc_scratch_bytes(void) { return (int64_t)cross_attention_tc_scratch_bytes() + 256; }
+
+int b200w_cross_attention_tc(const void* cross_kv_dev, int n_streams, int n_layers, int layer, int n_heads, int len,
+                             const void* q_dev, const int32_t* stream_dev, const int32_t* g_start_dev,
+                             const int32_t* g_count_dev, const int32_t* n_live_dev, int n_groups, void* out_dev,
+                             float scale, void* scratch_dev, void* stream) {
+  B200W_API_BEGIN
+  cross_attention_tc(static_cast<const bf16*>(cross_kv_dev), n_streams, n_layers, layer, n_heads, len,
+                     static_cast<const bf16*>(q_dev), n_heads * 64, stream_dev, g_start_dev, g_count_dev, n_live_dev,
+                     n_groups, static_cast<bf16*>(out_dev), n_heads * 64, scale, scratch_dev,
+                     static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
 int b200w_conv1d_k3(const void* x_dev, const void* w_dev, const float* bias_dev,
                     const float* addend_dev, void* out_dev, int B, int T, int C, int N, int stride,
                     int out_fp32, void* stream) {

@@ -132,3 +132,50 @@ def test_skinny_gemm(lib, cuda_device, M, N, K, splits):
     torch.cuda.synchronize()
     refg = torch.nn.functional.gelu(ref + bias)
     assert (out16[:, :N].float() - refg).abs().max().item() <= 2e-2 * max(1.0, refg.abs().max().item())
+
+
+@pytest.mark.parametrize("n_streams,H,L,layer,length,counts", [
+    (2, 6, 2, 1, 1500, [5, 5]),                 # two streams, beam 5: 12 items, all split into key-range pieces
+    (32, 20, 1, 0, 1500, [5] * 32),             # the bench shape: 640 items = whole rounds + split tail round
+    (3, 4, 1, 0, 1500, [1, 8, 0]),              # greedy row, full group of 8, finished stream (skipped)
+    (2, 8, 1, 0, 700, [3, 2]),                  # ragged key count (6 tiles, last one partly out of range)
+    (40, 8, 1, 0, 1500, [5] * 40),              # 320 items > 296 CTAs with remainder
+])
+def test_cross_attention_tc(lib, cuda_device, n_streams, H, L, layer, length, counts):
+    """Decode-step cross attention (tcgen05) vs fp32 softmax(q k^T / 8) v on the same bf16 inputs."""
+    g = torch.Generator(device="cpu").manual_seed(n_streams * 131 + H + length)
+    d = H * 64
+    kv = (torch.randn(n_streams, L, 2, H, length, 64, generator=g)).to(torch.bfloat16).to(cuda_device)
+    rows_per = 8
+    n_rows = n_streams * rows_per
+    q = (torch.randn(n_rows, d, generator=g) * 1.5).to(torch.bfloat16).to(cuda_device)
+    stream = torch.arange(n_streams, dtype=torch.int32).repeat_interleave(rows_per).to(cuda_device)
+    live = [i for i, c in enumerate(counts) if c > 0]
+    dead = [i for i, c in enumerate(counts) if c == 0]
+    order = live + dead  # live groups first, as the engine orders them
+    g_start = torch.tensor([i * rows_per for i in order], dtype=torch.int32, device=cuda_device)
+    g_count = torch.tensor([counts[i] for i in order], dtype=torch.int32, device=cuda_device)
+    n_live = torch.tensor([len(live)], dtype=torch.int32, device=cuda_device)
+    out = torch.full((n_rows, d), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    scratch = torch.zeros(lib.b200w_cross_attention_tc_scratch_bytes(), dtype=torch.uint8, device=cuda_device)
+    for _ in range(2):  # twice: the arrival counters of split items must reset themselves
+        _lib.check(lib.b200w_cross_attention_tc(kv.data_ptr(), n_streams, L, layer, H, length, q.data_ptr(),
+                                                stream.data_ptr(), g_start.data_ptr(), g_count.data_ptr(),
+                                                n_live.data_ptr(), len(counts), out.data_ptr(), 0.125,
+                                                scratch.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    worst = 0.0
+    for s_i, c in enumerate(counts):
+        r0 = s_i * rows_per
+        if c == 0:
+            assert (out[r0:r0 + rows_per].float() == 7.0).all(), "rows of a finished stream must not be written"
+            continue
+        qs = q[r0:r0 + c].float().view(c, H, 64).transpose(0, 1)          # [H][c][64]
+        k = kv[s_i, layer, 0].float()                                      # [H][len][64]
+        v = kv[s_i, layer, 1].float()
+        ref = torch.softmax(qs @ k.transpose(-1, -2) * 0.125, dim=-1) @ v  # [H][c][64]
+        ref = ref.transpose(0, 1).reshape(c, d)
+        worst = max(worst, (out[r0:r0 + c].float() - ref).abs().max().item())
+        assert (out[r0 + c:r0 + rows_per].float() == 7.0).all(), "dead rows of a live group must not be written"
+    # P is rounded to bf16 before P.V and the output is bf16: |v| <~ 4, so 2^-8 relative of a few units
+    assert worst <= 3e-2, f"max abs err {worst}"
