@@ -236,12 +236,14 @@ template <int NW>
 __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p) {
   extern __shared__ float s_dyn[];  // [max_len] table (int) | [NW][max_len] scores
   pdl_trigger();
-  pdl_wait();
   const int qi = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y * NW + warp;
   int* s_tab = reinterpret_cast<int*>(s_dyn);
   float* sc = s_dyn + p.max_len + warp * p.max_len;
+  // The pass metadata and the page table were written by the first kernels of the pass, many launches
+  // ago (every launch in between completed before this grid could start): reading them ahead of the
+  // dependency wait is safe and takes one L2 round trip off the critical path.  q, K and V are not.
   const int len = p.kvlen[qi];
   const int tr = p.trow[qi];
   const long long base = p.kv_base_off ? p.kv_base_off[tr] : 0;
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p
     const int* tab = p.table ? p.table + (long long)tr * p.table_stride : nullptr;
     for (int i = threadIdx.x; i < len; i += NW * 32) s_tab[i] = tab ? tab[i] : i;
   }
+  pdl_wait();
   // q in registers (every lane holds the whole 64-vector, pre-scaled)
   float q[HD];
   {

@@ -227,12 +227,15 @@ __global__ void __launch_bounds__(256) split_finalize_kernel(const float* __rest
                                                              const int* __restrict__ slot, bf16* __restrict__ kpool,
                                                              bf16* __restrict__ vpool, int d) {
   pdl_trigger();
-  pdl_wait();
   const int row = blockIdx.x;
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < N) a = __ldg(reinterpret_cast<const float4*>(bias + c));  // weights: safe ahead of the wait
+  long long sl = 0;
+  if (slot) sl = slot[row];  // pass metadata: written long before the kernel ahead of this one started
+  pdl_wait();
   if (c >= N) return;
   const float* pp = partial + (long long)row * N + c;
-  float4 a = __ldg(reinterpret_cast<const float4*>(bias + c));
 #pragma unroll 4
   for (int s = 0; s < n_splits; ++s) {
     const float4 v = *reinterpret_cast<const float4*>(pp + s * stride);
@@ -245,7 +248,6 @@ __global__ void __launch_bounds__(256) split_finalize_kernel(const float* __rest
   u.y = *reinterpret_cast<uint32_t*>(&hi);
   bf16* dst = out + (long long)row * ldo + c;
   if (slot && c >= d) {
-    const long long sl = slot[row];
     dst = c < 2 * d ? kpool + sl * d + (c - d) : vpool + sl * d + (c - 2 * d);
   }
   *reinterpret_cast<uint2*>(dst) = u;

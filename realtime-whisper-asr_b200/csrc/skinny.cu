@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include <map>
+#include <mutex>
 #include <tuple>
 
 #include "gemm.h"
@@ -275,6 +276,8 @@ void skinny_gemm(const SkinnyDesc& d, cudaStream_t stream) {
     }
   };
   static std::map<Key, SkinnyLaunch*> cache;
+  static std::mutex cache_mutex;  // engines may be driven from several host threads
+  std::lock_guard<std::mutex> lock(cache_mutex);
   const Key key{d.X, d.W, d.bias, d.out, d.ldx, d.ldw, d.ldo, d.split_stride, d.M, d.N, d.K, d.act, d.out_fp32, splits, p.tile_rows, g_sk_trace};
   auto it = cache.find(key);
   if (it == cache.end()) {
