@@ -231,19 +231,18 @@ void enc_attention(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out,
 // ------------------------------------------------------------------------------ decoder attention
 // One CTA per (query, group of NW heads), one warp per head.  The query's page-table row is staged
 // in shared memory once (all heads of a query share it), so the K and V row loads do not wait on a
-// table load each: a warp keeps one 128-byte K row per lane, then 16 V rows, in flight at a time.
+// table load each: a warp keeps one 128-byte K row per lane, then 16 V rows, in flight at a time (two K rows per lane /
+// 32 V rows measured slower: more registers, fewer resident CTAs).
 template <int NW>
 __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p) {
   extern __shared__ float s_dyn[];  // [max_len] table (int) | [NW][max_len] scores
   pdl_trigger();
+  pdl_wait();
   const int qi = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y * NW + warp;
   int* s_tab = reinterpret_cast<int*>(s_dyn);
   float* sc = s_dyn + p.max_len + warp * p.max_len;
-  // The pass metadata and the page table were written by the first kernels of the pass, many launches
-  // ago (every launch in between completed before this grid could start): reading them ahead of the
-  // dependency wait is safe and takes one L2 round trip off the critical path.  q, K and V are not.
   const int len = p.kvlen[qi];
   const int tr = p.trow[qi];
   const long long base = p.kv_base_off ? p.kv_base_off[tr] : 0;
@@ -253,7 +252,6 @@ __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p
     const int* tab = p.table ? p.table + (long long)tr * p.table_stride : nullptr;
     for (int i = threadIdx.x; i < len; i += NW * 32) s_tab[i] = tab ? tab[i] : i;
   }
-  pdl_wait();
   // q in registers (every lane holds the whole 64-vector, pre-scaled)
   float q[HD];
   {
@@ -272,33 +270,28 @@ __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p
   }
   __syncthreads();
   float mx = -INFINITY;
-  for (int i0 = lane; i0 < len; i0 += 64) {  // two keys per lane per round: 16 independent 16-byte loads in flight
-    const int i1 = i0 + 32;
-    const bool has1 = i1 < len;
-    const bf16* kp0 = kb + (long long)s_tab[i0] * p.kv_row_stride;
-    const bf16* kp1 = kb + (long long)s_tab[has1 ? i1 : i0] * p.kv_row_stride;
-    uint4 kr0[8], kr1[8];
+  for (int i = lane; i < len; i += 32) {
+    const long long roff = (long long)s_tab[i] * p.kv_row_stride;
+    const bf16* kp = kb + roff;
+    uint4 kr[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) kr0[c] = __ldg(reinterpret_cast<const uint4*>(kp0) + c);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) kr1[c] = __ldg(reinterpret_cast<const uint4*>(kp1) + c);
-    float a0 = 0.f, a1 = 0.f;
+    for (int c = 0; c < 8; ++c) kr[c] = __ldg(reinterpret_cast<const uint4*>(kp) + c);
+    // the value row of the same key (one 128-byte line) is needed right after the softmax: start
+    // pulling it into L2 now, so that the P.V loop does not pay HBM latency per batch of rows
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + roff));
+    float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const __nv_bfloat162* u0 = reinterpret_cast<const __nv_bfloat162*>(&kr0[c]);
-      const __nv_bfloat162* u1 = reinterpret_cast<const __nv_bfloat162*>(&kr1[c]);
+      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&kr[c]);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float2 f0 = __bfloat1622float2(u0[t]), f1 = __bfloat1622float2(u1[t]);
-        a0 = fmaf(q[8 * c + 2 * t], f0.x, a0);
-        a0 = fmaf(q[8 * c + 2 * t + 1], f0.y, a0);
-        a1 = fmaf(q[8 * c + 2 * t], f1.x, a1);
-        a1 = fmaf(q[8 * c + 2 * t + 1], f1.y, a1);
+        const float2 f = __bfloat1622float2(u2[t]);
+        acc = fmaf(q[8 * c + 2 * t], f.x, acc);
+        acc = fmaf(q[8 * c + 2 * t + 1], f.y, acc);
       }
     }
-    sc[i0] = a0;
-    mx = fmaxf(mx, a0);
-    if (has1) { sc[i1] = a1; mx = fmaxf(mx, a1); }
+    sc[i] = acc;
+    mx = fmaxf(mx, acc);
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.f;
@@ -320,13 +313,13 @@ __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p
   float2 acc = make_float2(0.f, 0.f);
   const bf16* vl = vb + 2 * lane;
   int i = 0;
-  for (; i + 32 <= len; i += 32) {  // 32 independent 128-byte row reads in flight per warp
-    __nv_bfloat162 v[32];
+  for (; i + 16 <= len; i += 16) {  // 16 independent 128-byte row reads in flight per warp
+    __nv_bfloat162 v[16];
 #pragma unroll
-    for (int u = 0; u < 32; ++u)
+    for (int u = 0; u < 16; ++u)
       v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)s_tab[i + u] * p.kv_row_stride);
 #pragma unroll
-    for (int u = 0; u < 32; ++u) {
+    for (int u = 0; u < 16; ++u) {
       const float pw = sc[i + u];
       const float2 f = __bfloat1622float2(v[u]);
       acc.x = fmaf(pw, f.x, acc.x);
@@ -334,12 +327,12 @@ __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p
     }
   }
   {  // ragged tail: still all loads first
-    __nv_bfloat162 v[32];
+    __nv_bfloat162 v[16];
 #pragma unroll
-    for (int u = 0; u < 32; ++u)
+    for (int u = 0; u < 16; ++u)
       if (i + u < len) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)s_tab[i + u] * p.kv_row_stride);
 #pragma unroll
-    for (int u = 0; u < 32; ++u)
+    for (int u = 0; u < 16; ++u)
       if (i + u < len) {
         const float2 f = __bfloat1622float2(v[u]);
         acc.x = fmaf(sc[i + u], f.x, acc.x);
