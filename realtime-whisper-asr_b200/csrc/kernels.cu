@@ -10,7 +10,8 @@ namespace b200w {
 // exact-erf GELU (Abramowitz-Stegun 7.1.26), same arithmetic as the GEMM epilogue (ptx.cuh)
 __device__ __forceinline__ float gelu_erf_k(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;  // 1 / (1 + p z): MUFU reciprocal (1 ulp) instead of the IEEE-rounded sequence
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
