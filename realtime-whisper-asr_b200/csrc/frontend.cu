@@ -136,31 +136,43 @@ __global__ void __launch_bounds__(256) logmel_kernel(const MelTables* __restrict
   const long long Lz = N + HOP;  // audio zero-padded by one hop
   const int n_mels = tab->n_mels;
 
-  for (int i = tid; i < NFFT; i += 256) s_win[i] = tab->window[i];
-  for (int i = tid; i < 200; i += 256) s_tw200[i] = tab->tw200[i];
-  if (tid < 25) s_tw25[tid] = tab->tw25[tid];
-  if (tid < 101) s_tw400[tid] = tab->tw400[tid];
-  for (int i = tid; i < 512; i += 256) s_melw[i] = tab->mel_w[i];
+  // constant tables: global -> shared with cp.async as well (they share the wait below with the samples)
+  auto cp4 = [](void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+  };
+  auto cp8 = [](void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+  };
+  for (int i = tid; i < NFFT; i += 256) cp4(s_win + i, tab->window + i);
+  for (int i = tid; i < 200; i += 256) cp8(s_tw200 + i, tab->tw200 + i);
+  if (tid < 25) cp8(s_tw25 + tid, tab->tw25 + tid);
+  if (tid < 101) cp8(s_tw400 + tid, tab->tw400 + tid);
+  for (int i = tid; i < 512; i += 256) cp4(s_melw + i, tab->mel_w + i);
   if (tid < 128) {
-    s_mello[tid] = tab->mel_lo[tid];
-    s_melcnt[tid] = tab->mel_cnt[tid];
-    s_melwoff[tid] = tab->mel_woff[tid];
+    cp4(s_mello + tid, tab->mel_lo + tid);
+    cp4(s_melcnt + tid, tab->mel_cnt + tid);
+    cp4(s_melwoff + tid, tab->mel_woff + tid);
   }
   if (tid == 0) s_blockmax = float_to_ordered(-INFINITY);
 
   // samples of the tile (coalesced), boundary rules resolved here
   const long long g0 = (long long)f0 * HOP - NFFT / 2;
+  // In-range samples go global -> shared with cp.async (no register round trip, so all ~21 requests of a
+  // thread are in flight together: the first version waited on DRAM once per 4 samples); only the
+  // reflected / zero-padded borders of a clip take the scalar path.
   for (int i = tid; i < TILE_SAMPLES; i += 256) {
     const long long g = g0 + i;
-    float v = 0.f;
     if (g >= 0 && g < N) {
-      v = __ldg(a.audio + off + g);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_x + i);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(a.audio + off + g) : "memory");
     } else {
+      float v = 0.f;
       const long long r = reflect_index(g, Lz);
       if (r < N) v = __ldg(a.audio + off + r);
+      s_x[i] = v;
     }
-    s_x[i] = v;
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   const int nf = min(FT, n_frames - f0);  // valid frames in this tile
