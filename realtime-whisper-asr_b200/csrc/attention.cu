@@ -23,6 +23,12 @@ struct EncAttnParams {
   int T, d;
   float scale_log2e;
   bf16* out;  // [B][T][d]
+  // cross-attention mode (seg_start != null): grid.z walks segments = runs of query rows of one stream;
+  // Q rows come from a [rows][d] activation, K/V from the per-chunk cross K/V blocks [block][T][64]
+  const int* seg_start;
+  const int* seg_count;
+  const int* row_stream;
+  int blocks_per_stream, layer_block0, n_heads;
 };
 
 // KT = keys per inner block (64 or 128).  Smaller blocks mean less shared memory and TMEM per CTA,
@@ -48,6 +54,16 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
   const uint32_t barQ = smem_u32(bars), barK = smem_u32(bars + 1), barV = smem_u32(bars + 2),
                  barS = smem_u32(bars + 3), barO = smem_u32(bars + 4);
+  // cross mode: this CTA's query rows are [row0 + q0, row0 + n_rows) of the activation
+  const bool cross = p.seg_start != nullptr;
+  int row0 = 0, n_rows = p.T;
+  if (cross) {
+    pdl_trigger();
+    pdl_wait();
+    row0 = p.seg_start[b];
+    n_rows = p.seg_count[b];
+    if (q0 >= n_rows) return;  // before any barrier / TMEM use: whole CTA leaves
+  }
 
   if (tid == 0) {
     mbar_init(barQ, 1);
@@ -71,15 +87,24 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
 
   const int nblk = (p.T + KT - 1) / KT;
-  const int colQ = h * HD, colK = p.d + h * HD, colV = 2 * p.d + h * HD;
+  // self (encoder): Q, K, V are column ranges of the fused QKV activation of window b.
+  // cross: Q = activation rows, K and V = [T][64] blocks (stream, layer, k|v, head) of the cross K/V buffer.
+  const int colQ = h * HD;
+  const int colK = cross ? 0 : p.d + h * HD, colV = cross ? 0 : 2 * p.d + h * HD;
+  const int rowQ = row0 + q0, zQ = cross ? 0 : b;
+  int zK = b, zV = b;
+  if (cross) {
+    zK = p.row_stream[row0] * p.blocks_per_stream + p.layer_block0 + h;
+    zV = zK + p.n_heads;
+  }
 
   if (tid == 0) {
     mbar_arrive_expect_tx(barQ, TILE_BYTES);
-    tma_load_3d(smem_u32(sQ), &tmQ, barQ, colQ, q0, b);
+    tma_load_3d(smem_u32(sQ), &tmQ, barQ, colQ, rowQ, zQ);
     mbar_arrive_expect_tx(barK, KV_BYTES);
-    tma_load_3d(smem_u32(sK), &tmKV, barK, colK, 0, b);
+    tma_load_3d(smem_u32(sK), &tmKV, barK, colK, 0, zK);
     mbar_arrive_expect_tx(barV, KV_BYTES);
-    tma_load_3d(smem_u32(sV), &tmKV, barV, colV, 0, b);
+    tma_load_3d(smem_u32(sV), &tmKV, barV, colV, 0, zV);
   }
 
   constexpr uint32_t idescS = make_idesc_bf16(128, KT, 0, 0);  // Q (K-major) x K (K-major)
@@ -107,7 +132,7 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     if (tid == 0 && j + 1 < nblk) {  // K tile is free again: prefetch the next one
       mbar_arrive_expect_tx(barK, KV_BYTES);
-      tma_load_3d(smem_u32(sK), &tmKV, barK, colK, (j + 1) * KT, b);
+      tma_load_3d(smem_u32(sK), &tmKV, barK, colK, (j + 1) * KT, zK);
     }
     const int kv_valid = min(KT, p.T - j * KT);
     // one pass over the 64 scores of this block, held in registers:
@@ -167,7 +192,7 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     if (tid == 0 && j + 1 < nblk) {
       mbar_arrive_expect_tx(barV, KV_BYTES);
-      tma_load_3d(smem_u32(sV), &tmKV, barV, colV, (j + 1) * KT, b);
+      tma_load_3d(smem_u32(sV), &tmKV, barV, colV, (j + 1) * KT, zV);
     }
 #pragma unroll
     for (int c0 = 0; c0 < HD; c0 += 32) {
@@ -182,9 +207,9 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 
   const int t = q0 + r;
-  if (t < p.T) {
+  if (t < n_rows) {
     const float inv = 1.0f / l_run;
-    bf16* dst = p.out + ((long long)b * p.T + t) * p.d + h * HD;
+    bf16* dst = p.out + (cross ? (long long)(row0 + t) : (long long)b * p.T + t) * p.d + h * HD;
 #pragma unroll
     for (int c = 0; c < HD; c += 8) {
       uint4 u;
@@ -216,7 +241,7 @@ static void launch_enc_attn(const bf16* qkv, int B, int T, int d, int n_heads, b
                                           smem_bytes));
     configured = true;
   }
-  EncAttnParams p{T, d, 0.125f * 1.4426950408889634f, out};
+  EncAttnParams p{T, d, 0.125f * 1.4426950408889634f, out, nullptr, nullptr, nullptr, 0, 0, n_heads};
   enc_attn_kernel<KT, CTAS><<<dim3(cdiv(T, QT), n_heads, B), 128, smem_bytes, stream>>>(tmQ, tmKV, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
@@ -226,6 +251,31 @@ void enc_attention(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out,
   B200W_REQUIRE(d == n_heads * HD, "head dim must be 64");
   if (B <= 0) return;
   launch_enc_attn<64, 3>(qkv, B, T, d, n_heads, out, stream);
+}
+
+// Cross attention for passes with many query rows per stream (prompts, the teacher-forced alignment pass):
+// the same flash kernel, one CTA per (128 query rows of a segment, head): every segment streams its K/V
+// once instead of once per group of 8 rows.
+void cross_attention_flash(const bf16* cross_kv, int n_streams, int n_layers, int layer, int n_heads, int len,
+                           const bf16* q, int n_q_rows, const int* row_stream, const int* seg_start,
+                           const int* seg_count, int n_segs, int max_seg_rows, bf16* out, cudaStream_t stream) {
+  if (n_segs <= 0) return;
+  const int d = n_heads * HD;
+  CUtensorMap tmQ, tmKV;
+  make_tmap_bf16_3d(&tmQ, q, d, n_q_rows, 1, d, (uint64_t)n_q_rows * d, HD, 128);
+  make_tmap_bf16_3d(&tmKV, cross_kv, HD, len, (uint64_t)n_streams * n_layers * 2 * n_heads, HD, (uint64_t)len * HD, HD, 64);
+  constexpr int smem_bytes = TILE_BYTES + 2 * 64 * HD * 2 + 128 * 64 * 2 + 5 * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200W_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  EncAttnParams p{len, d, 0.125f * 1.4426950408889634f, out, seg_start, seg_count, row_stream,
+                  n_layers * 2 * n_heads, 2 * layer * n_heads, n_heads};
+  launch_pdl(enc_attn_kernel<64, 3>, dim3(cdiv(max_seg_rows, QT), n_heads, n_segs), dim3(128), (size_t)smem_bytes, stream,
+             tmQ, tmKV, p);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------ decoder attention

@@ -64,6 +64,12 @@ void cross_attention(const CrossAttnParams& p, int n_groups, int n_heads, int ma
 size_t cross_attention_scratch_bytes(int n_groups, int n_heads);
 static constexpr int CROSS_GROUP = 8;
 
+// Cross attention for passes with many rows per stream (prompts, alignment): flash kernel (tcgen05), one CTA per
+// (128 query rows of a segment, head).  Segments = runs of consecutive query rows of one stream.
+void cross_attention_flash(const bf16* cross_kv, int n_streams, int n_layers, int layer, int n_heads, int len,
+                           const bf16* q, int n_q_rows, const int* row_stream, const int* seg_start,
+                           const int* seg_count, int n_segs, int max_seg_rows, bf16* out, cudaStream_t stream);
+
 // Decode-step cross attention on tcgen05 (no probability export).  cross_kv is the whole per-chunk
 // buffer [n_streams][n_layers][k|v][n_heads][len][64]; groups [0, *n_live_groups) are processed, each
 // with g_count <= 8 live rows starting at g_start.

@@ -337,6 +337,8 @@ struct PassMeta {  // device pointers into e->meta for one forward pass of n tok
   int *g_start, *g_count;  // cross-attention groups: runs of <= 8 rows of one stream (live groups first)
   int* n_live = nullptr;   // device: number of groups with at least one live row
   int n_live_host = 0;
+  int *seg_start = nullptr, *seg_count = nullptr;  // runs of consecutive rows of one stream (flash cross attention)
+  int n_segs = 0, max_seg = 0;
   int n_groups = 0, max_group = 1;
   int4* state;
 };
@@ -393,7 +395,18 @@ PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) 
     gs.swap(gs2);
     gc.swap(gc2);
   }
-  const size_t ints = (size_t)n * 7 + 2 * (size_t)ng + 1, bytes = ints * 4 + (size_t)n * 16 + 16;
+  // segments: maximal runs of consecutive rows of one stream (idle padding rows included: only many-row passes,
+  // which have none, use them)
+  std::vector<int> ss, sc;
+  for (int i = 0; i < n;) {
+    int j = i + 1;
+    while (j < n && h.stream[j] == h.stream[i]) ++j;
+    ss.push_back(i);
+    sc.push_back(j - i);
+    i = j;
+  }
+  const int nseg = (int)ss.size();
+  const size_t ints = (size_t)n * 7 + 2 * (size_t)ng + 1 + 2 * (size_t)nseg, bytes = ints * 4 + (size_t)n * 16 + 16;
   e->h_meta.alloc(bytes);
   int* hp = e->h_meta.as<int>();
   memcpy(hp, h.tok.data(), n * 4);
@@ -406,6 +419,8 @@ PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) 
   memcpy(hp + 7 * n, gs.data(), ng * 4);
   memcpy(hp + 7 * n + ng, gc.data(), ng * 4);
   hp[7 * n + 2 * ng] = n_live;
+  memcpy(hp + 7 * n + 2 * ng + 1, ss.data(), nseg * 4);
+  memcpy(hp + 7 * n + 2 * ng + 1 + nseg, sc.data(), nseg * 4);
   const size_t st_off = (ints * 4 + 15) / 16 * 16;
   memcpy(reinterpret_cast<char*>(hp) + st_off, h.state.data(), (size_t)n * 16);
   *copy_bytes = st_off + (size_t)n * 16;
@@ -420,6 +435,11 @@ PassMeta fill_host_meta(b200w_engine* e, const HostMeta& h, size_t* copy_bytes) 
   m.n_groups = ng;
   m.n_live = dp + 7 * n + 2 * ng;
   m.n_live_host = n_live;
+  m.seg_start = dp + 7 * n + 2 * ng + 1;
+  m.seg_count = m.seg_start + nseg;
+  m.n_segs = nseg;
+  m.max_seg = 0;
+  for (int c : sc) m.max_seg = std::max(m.max_seg, c);
   m.max_group = max_cap;  // capacity, not the live count: keeps the launch shape fixed
   m.state = reinterpret_cast<int4*>(reinterpret_cast<char*>(dp) + st_off);
   return m;
@@ -515,7 +535,16 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
       // prompt / alignment passes are timed under "other"
       if (step_tc) g_optimer.next_work = (double)m.n_live_host * e->H * 2.0 * e->Tenc * HEAD_DIM * 2.0;
       OpScope _op_scope_x(step_tc ? 7 : 15, s);
-      if (tc) {
+      // many rows per stream (prompts, alignment): flash kernel, K/V streamed once per (stream, head)
+      static const bool use_flash = getenv("B200W_NO_CROSS_FLASH") == nullptr;
+      if (use_flash && !e->step_pass && m.max_seg > CROSS_GROUP) {
+        cross_attention_flash(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, n, m.stream, m.seg_start,
+                              m.seg_count, m.n_segs, m.max_seg, attn, s);
+        if (c.head_export) {
+          c.export_only = 1;
+          cross_attention(c, m.n_groups, e->H, m.max_group, s, nullptr);
+        }
+      } else if (tc) {
         cross_attention_tc(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, d, m.stream, m.g_start, m.g_count,
                            m.n_live, m.n_groups, attn, d, 0.125f, e->x_tc.p, s);
         if (c.head_export) {
@@ -684,7 +713,7 @@ int b200w_engine_finalize(b200w_engine* e) {
   e->logit_rows = (int)std::max<int64_t>(2 * rows, 1024);
   e->logits.alloc((size_t)e->logit_rows * e->ldv * 4);
   e->d_hsel.alloc((size_t)e->logit_rows * d * 2);
-  e->meta.alloc((size_t)n * 9 * 4 + (size_t)n * 16 + 64);
+  e->meta.alloc((size_t)n * 12 * 4 + (size_t)n * 16 + 64);
   e->scratch_i.alloc(((size_t)e->logit_rows + 4 * Bm + n) * 4);
   e->cross_off.alloc(Bm * 8);
   e->const_len.alloc(n * 4);
@@ -701,7 +730,7 @@ int b200w_engine_finalize(b200w_engine* e) {
     B200W_CHECK_CUDA(cudaMemcpy(e->const_len.p, cl.data(), n * 4, cudaMemcpyHostToDevice));
   }
   // pinned staging buffers get their final size here: captured decode graphs hold their addresses
-  e->h_meta.alloc((size_t)n * 9 * 4 + (size_t)n * 16 + 64);
+  e->h_meta.alloc((size_t)n * 12 * 4 + (size_t)n * 16 + 64);
   e->h_out.alloc(std::max<size_t>({(size_t)rows * MAX_TOPK * 8 + 64, (size_t)Bm * (e->Tctx + T + 4) * 8 + Bm * 8,
                                    (size_t)Bm * 128 * 4}));
   B200W_CHECK_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
