@@ -53,11 +53,14 @@ struct __align__(128) SkinnyLaunch {
   SkinnyParams p;
 };
 
-// Plain spin (no watchdog): this kernel is launch-latency critical and every instruction of code
+// Out-of-line spin with a cheap spin-count watchdog: this kernel is launch-latency critical and every instruction of code
 // has to be fetched from L2 by every freshly launched CTA (measured: ~1 us per 16 KB of executed
 // straight-line code), so everything here is kept small and un-unrolled where it can be.
 __device__ __noinline__ void sk_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins == (1u << 28)) __trap();  // a protocol bug must fault (launch error), never hang the GPU
+  }
 }
 
 // ACT: 0 none, 1 exact-erf GELU.  OUT_FP32: fp32 (split partial sums / logits) or bf16.

@@ -10,7 +10,7 @@ reference reaches at /root/reference/asr_components.py:279-288). 
 from __future__ import annotations
 
 import string
-from functools import cached_property
+from functools import cached_property, lru_cache
 from typing import List, Optional, Sequence, Tuple
 
 LANGUAGES = (
@@ -27,6 +27,7 @@ class _ByteVocab:
         return list(text.encode("utf-8"))
 
     @staticmethod
+    @lru_cache(maxsize=None)
     def _piece(i: int) -> bytes:
         if i < 256:
             return bytes([i])
