@@ -108,6 +108,14 @@ int b200w_cross_attention_tc(const void* cross_kv_dev, int n_streams, int n_laye
                              const int32_t* g_count_dev, const int32_t* n_live_dev, int n_groups, void* out_dev,
                              float scale, void* scratch_dev, void* stream);
 
+/* Cross attention for passes with many query rows per stream (prompts, alignment): flash kernel, one CTA per
+ * (128 query rows of a segment, head).  Segments = runs of consecutive query rows of one stream.
+ *   q_dev bf16 [n_q_rows][n_heads*64]   row_stream_dev int32 [n_q_rows]   seg_start_dev / seg_count_dev int32 [n_segs] */
+int b200w_cross_attention_flash(const void* cross_kv_dev, int n_streams, int n_layers, int layer, int n_heads, int len,
+                                const void* q_dev, int n_q_rows, const int32_t* row_stream_dev,
+                                const int32_t* seg_start_dev, const int32_t* seg_count_dev, int n_segs,
+                                int max_seg_rows, void* out_dev, void* stream);
+
 /* conv1d (kernel 3, padding 1, stride 1 or 2) as implicit GEMM over time-major activations:
  * x bf16 [B][T][C] -> GELU(conv(x) + bias) (+ addend fp32 [T_out][N], e.g. positions) ->
  * out [B][T_out][N] bf16 or fp32.  w bf16 [N][3*C] tap-major.  C % 64 == 0. */

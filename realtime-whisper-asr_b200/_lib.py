@@ -54,6 +54,7 @@ SIGNATURES = {
     "b200w_skinny_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _vp]),
     "b200w_cross_attention_tc_scratch_bytes": (C.c_int64, []),
     "b200w_cross_attention_tc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _f, _vp, _vp]),
+    "b200w_cross_attention_flash": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "b200w_conv1d_k3": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200w_enc_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "b200w_engine_create": (_i, [C.POINTER(ModelConfig), C.POINTER(_vp)]),

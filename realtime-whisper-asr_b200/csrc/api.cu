@@ -164,6 +164,17 @@ int b200w_cross_attention_tc(const void* cross_kv_dev, int n_streams, int n_laye
   B200W_API_END
 }
 
+int b200w_cross_attention_flash(const void* cross_kv_dev, int n_streams, int n_layers, int layer, int n_heads, int len,
+                                const void* q_dev, int n_q_rows, const int32_t* row_stream_dev,
+                                const int32_t* seg_start_dev, const int32_t* seg_count_dev, int n_segs,
+                                int max_seg_rows, void* out_dev, void* stream) {
+  B200W_API_BEGIN
+  cross_attention_flash(static_cast<const bf16*>(cross_kv_dev), n_streams, n_layers, layer, n_heads, len,
+                        static_cast<const bf16*>(q_dev), n_q_rows, row_stream_dev, seg_start_dev, seg_count_dev, n_segs,
+                        max_seg_rows, static_cast<bf16*>(out_dev), static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
 int b200w_conv1d_k3(const void* x_dev, const void* w_dev, const float* bias_dev,
                     const float* addend_dev, void* out_dev, int B, int T, int C, int N, int stride,
                     int out_fp32, void* stream) {

@@ -907,6 +907,7 @@ struct CrossTcParams {
   bf16* out;
   int out_stride;
   float scale_log2e;
+  int allow_split;  // 0: every item is computed whole (results do not depend on how many items share the launch)
   float* partial;  // [grid][XT_MAX_PIECES][XT_PART_FLOATS]
   int* counters;   // [grid], zero between launches
   long long* trace;  // development aid: [cta][unit < 6][8] clock64 stamps, or null
@@ -917,7 +918,7 @@ struct XtUnit {
   int item, t0, t1, piece, n_pieces, tail_idx;
 };
 // u-th unit of this CTA (every role evaluates the same sequence)
-__device__ __forceinline__ bool xt_unit(int u, int n_items, int n_tiles, XtUnit& un) {
+__device__ __forceinline__ bool xt_unit(int u, int n_items, int n_tiles, XtUnit& un, int allow_split = 1) {
   const int G = gridDim.x, R = n_items / G, r = n_items - R * G;
   if (u < R) {
     un.item = blockIdx.x + u * G;
@@ -926,8 +927,9 @@ __device__ __forceinline__ bool xt_unit(int u, int n_items, int n_tiles, XtUnit&
   }
   if (u > R || r == 0) return false;
   int s = 1;
-  for (int d = 2; d <= XT_MAX_PIECES; ++d)
-    if (n_tiles % d == 0 && d * r <= G) s = d;
+  if (allow_split)
+    for (int d = 2; d <= XT_MAX_PIECES; ++d)
+      if (n_tiles % d == 0 && d * r <= G) s = d;
   if ((int)blockIdx.x >= r * s) return false;
   un.tail_idx = blockIdx.x / s;
   un.piece = blockIdx.x - un.tail_idx * s;
@@ -1033,7 +1035,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
   if (warp == 4) {
     if (lane == 0) {  // ---------------- TMA producer: K tiles then V tiles of every unit
       uint32_t slot = 0, phase = 0;
-      for (int u = 0; xt_unit(u, n_items, n_tiles, un); ++u) {
+      for (int u = 0; xt_unit(u, n_items, n_tiles, un, p.allow_split); ++u) {
         const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
         const int blk = p.stream[p.g_start[g]] * p.blocks_per_stream + p.layer_block0 + h;
         for (int kv = 0; kv < 2; ++kv)
@@ -1047,7 +1049,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
       }
     } else {  // ---------------- lanes 1..31: stage the Q tile of unit `it` one unit ahead of its use
       pdl_wait();
-      for (int it = 0; xt_unit(it, n_items, n_tiles, un); ++it) {
+      for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.allow_split); ++it) {
         const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
         const int q0 = p.g_start[g], nq = p.g_count[g];
         uint4 u[5];
@@ -1077,7 +1079,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
       constexpr uint32_t idescS = make_idesc_bf16(128, 16, 0, 0);  // K (K-major) x Q (K-major)
       constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);  // P (K-major) x V (MN-major)
       uint32_t slot = 0, phase = 0;
-      for (int it = 0; xt_unit(it, n_items, n_tiles, un); ++it) {
+      for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.allow_split); ++it) {
         const int nt = un.t1 - un.t0;
         const uint32_t par = it & 1;
         mbar_wait(bar_q0 + 8 * par, (uint32_t)((it >> 1) & 1));
@@ -1113,7 +1115,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
   } else {  // ---------------- warps 0..3: softmax (thread = key row of every tile) and output
     pdl_wait();
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    for (int it = 0; xt_unit(it, n_items, n_tiles, un); ++it) {
+    for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.allow_split); ++it) {
       const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
       const int q0 = p.g_start[g], nq = p.g_count[g];
       const int nt = un.t1 - un.t0;
@@ -1267,7 +1269,7 @@ size_t cross_attention_tc_scratch_bytes() {
 void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int layer, int n_heads, int len,
                         const bf16* q, int q_stride, const int* stream, const int* g_start, const int* g_count,
                         const int* n_live_groups, int n_groups, bf16* out, int out_stride, float scale, void* scratch,
-                        cudaStream_t cs) {
+                        cudaStream_t cs, int allow_split) {
   if (n_groups <= 0) return;
   B200W_REQUIRE(len <= 128 * XT_MAX_TILES, "cross_attention_tc: at most 1536 keys");
   CUtensorMap tm;
@@ -1283,6 +1285,7 @@ void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int l
   p.n_live_groups = n_live_groups; p.n_heads = n_heads; p.blocks_per_stream = n_layers * 2 * n_heads;
   p.layer_block0 = 2 * layer * n_heads; p.len = len; p.out = out; p.out_stride = out_stride;
   p.scale_log2e = scale * 1.4426950408889634f;
+  p.allow_split = allow_split;
   // scratch: zero-initialised once by the owner; [num_sms counters][num_sms * pieces * record]
   p.counters = static_cast<int*>(scratch);
   p.partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + ((XT_CTAS_PER_SM * num_sms() * sizeof(int) + 255) & ~(size_t)255));

@@ -74,12 +74,13 @@ void cross_attention_flash(const bf16* cross_kv, int n_streams, int n_layers, in
 // buffer [n_streams][n_layers][k|v][n_heads][len][64]; groups [0, *n_live_groups) are processed, each
 // with g_count <= 8 live rows starting at g_start.
 void cross_tc_set_trace(void* dev_buf);  // development aid: per-item phase timestamps
+// allow_split = 0: no item is cut into key-range pieces (batch-size-invariant arithmetic; prompt / alignment passes).
 // scratch: cross_attention_tc_scratch_bytes() + 256 bytes, zeroed once (split-item partial results and
 // their self-resetting arrival counters).
 size_t cross_attention_tc_scratch_bytes();
 void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int layer, int n_heads, int len,
                         const bf16* q, int q_stride, const int* stream, const int* g_start, const int* g_count,
                         const int* n_live_groups, int n_groups, bf16* out, int out_stride, float scale, void* scratch,
-                        cudaStream_t cs);
+                        cudaStream_t cs, int allow_split = 1);
 
 }  // namespace b200w

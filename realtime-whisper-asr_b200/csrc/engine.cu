@@ -299,7 +299,8 @@ SplitReduce skinny_split(b200w_engine* e, const bf16* A, int M, int K, const Lin
 
 SplitReduce residual_linear(b200w_engine* e, const bf16* A, int M, int K, const Lin& l, float* x, cudaStream_t s) {
   const int d = e->d;
-  if (use_skinny() && e->step_pass && d % 128 == 0) return skinny_split(e, A, M, K, l, d, 14, s);
+  // measured (tools/gemm_skinny_bench.py): 7 splits for K = d, 10 for K = 4d; more only adds slab traffic
+  if (use_skinny() && e->step_pass && d % 128 == 0) return skinny_split(e, A, M, K, l, d, K > 2 * d ? 10 : 7, s);
   const int splits = gemm_suggest_splits(M, d, K);
   if (splits <= 1 || (size_t)splits * M * d * 4 > e->d_split.bytes) {
     linear(A, M, K, l, d, x, d, 1, 0, x, 1, d, s);
@@ -501,7 +502,7 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     RUN(6) {
       OP(6);
       if (sk) {
-        const SplitReduce r = skinny_split(e, h, n, d, L.cq, d, 10, s);
+        const SplitReduce r = skinny_split(e, h, n, d, L.cq, d, 7, s);
         split_finalize(r.partial, r.n, r.stride, r.bias, n, d, 0, cq, d, nullptr, nullptr, nullptr, 0, s);
       } else {
         linear(h, n, d, L.cq, d, cq, d, 0, 0, nullptr, 0, 0, s);
@@ -546,7 +547,7 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
         }
       } else if (tc) {
         cross_attention_tc(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, d, m.stream, m.g_start, m.g_count,
-                           m.n_live, m.n_groups, attn, d, 0.125f, e->x_tc.p, s);
+                           m.n_live, m.n_groups, attn, d, 0.125f, e->x_tc.p, s, e->step_pass ? 1 : 0);
         if (c.head_export) {
           c.export_only = 1;
           cross_attention(c, m.n_groups, e->H, m.max_group, s, nullptr);
@@ -582,7 +583,22 @@ void logits_for_rows(b200w_engine* e, const int* sel_rows_dev, int n_sel, cudaSt
   Lin emb;
   emb.w = e->tok_emb;
   emb.b = nullptr;
-  RUN(11) { OP(11); linear(hsel, n_sel, e->d, emb, e->V, e->logits.p, e->ldv, 1, 0, nullptr, 0, 0, s); }
+  RUN(11) {
+    OP(11);
+    if (use_skinny() && e->step_pass && e->d % 128 == 0) {
+      // decode steps: the 133 MB embedding matrix is streamed once (the many-row kernel would stream it once per
+      // 128-row tile), 406 weight tiles of 128 vocabulary rows
+      for (int r0 = 0; r0 < n_sel; r0 += 256) {
+        SkinnyDesc g;
+        g.X = hsel + (long long)r0 * e->d; g.ldx = e->d; g.M = std::min(256, n_sel - r0);
+        g.W = emb.w; g.ldw = e->d; g.N = e->V; g.K = e->d;
+        g.out = e->logits.as<float>() + (long long)r0 * e->ldv; g.out_fp32 = 1; g.ldo = e->ldv;
+        skinny_gemm(g, s);
+      }
+    } else {
+      linear(hsel, n_sel, e->d, emb, e->V, e->logits.p, e->ldv, 1, 0, nullptr, 0, 0, s);
+    }
+  }
 }
 
 void upload_ints(int* dst, const std::vector<int>& v, cudaStream_t s) {
@@ -991,12 +1007,12 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     e->step_pass = true;
     try {
       decoder_forward(e, ckv, m, e->tables[from ^ 1].as<int>(), Tctx, nullptr, s);
+      logits_for_rows(e, nullptr, m.n, s);
     } catch (...) {
       e->step_pass = false;
       throw;
     }
     e->step_pass = false;
-    logits_for_rows(e, nullptr, m.n, s);
     SampleParams sps = sp;
     sps.state = m.state;
     RUN(12) { OP(12); sample_topk(sps, m.n, s); }

@@ -179,3 +179,36 @@ def test_cross_attention_tc(lib, cuda_device, n_streams, H, L, layer, length, co
         assert (out[r0 + c:r0 + rows_per].float() == 7.0).all(), "dead rows of a live group must not be written"
     # P is rounded to bf16 before P.V and the output is bf16: |v| <~ 4, so 2^-8 relative of a few units
     assert worst <= 3e-2, f"max abs err {worst}"
+
+
+@pytest.mark.parametrize("n_streams,H,L,layer,length,counts", [
+    (3, 6, 2, 1, 1500, [80, 5, 130]),              # > 128 rows in the last segment (two query tiles, ragged end)
+    (32, 20, 1, 0, 1500, [70 + (i % 7) for i in range(32)]),   # the alignment pass of the bench workload
+    (2, 4, 1, 0, 700, [9, 224]),                   # ragged key count; a long prompt
+])
+def test_cross_attention_flash(lib, cuda_device, n_streams, H, L, layer, length, counts):
+    """Many-row cross attention (flash kernel over activation-row queries and cross K/V blocks) vs fp32."""
+    g = torch.Generator(device="cpu").manual_seed(n_streams * 17 + H + length)
+    d = H * 64
+    kv = torch.randn(n_streams, L, 2, H, length, 64, generator=g).to(torch.bfloat16).to(cuda_device)
+    n_rows = sum(counts)
+    q = (torch.randn(n_rows, d, generator=g) * 1.5).to(torch.bfloat16).to(cuda_device)
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int32)
+    stream = torch.from_numpy(np.repeat(np.arange(n_streams, dtype=np.int32), counts)).to(cuda_device)
+    seg_start = torch.from_numpy(starts).to(cuda_device)
+    seg_count = torch.tensor(counts, dtype=torch.int32, device=cuda_device)
+    out = torch.full((n_rows, d), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    _lib.check(lib.b200w_cross_attention_flash(kv.data_ptr(), n_streams, L, layer, H, length, q.data_ptr(), n_rows,
+                                               stream.data_ptr(), seg_start.data_ptr(), seg_count.data_ptr(),
+                                               n_streams, max(counts), out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    worst = 0.0
+    for s_i, c in enumerate(counts):
+        r0 = int(starts[s_i])
+        qs = q[r0:r0 + c].float().view(c, H, 64).transpose(0, 1)
+        k = kv[s_i, layer, 0].float()
+        v = kv[s_i, layer, 1].float()
+        ref = (torch.softmax(qs @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).transpose(0, 1).reshape(c, d)
+        worst = max(worst, (out[r0:r0 + c].float() - ref).abs().max().item())
+    assert worst <= 3e-2, f"max abs err {worst}"
