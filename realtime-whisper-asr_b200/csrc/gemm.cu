@@ -39,6 +39,7 @@ struct GemmParams {
   int splits;      // split-K: > 1 => split s writes its partial sums (fp32) to out + s * split_stride
   long long split_stride;
   long long* trace;  // development aid (b200w_gemm_set_trace): 16 timestamps per CTA, or null
+  int v8ok;          // output / residual are 32-byte aligned: the fast epilogue may use 256-bit accesses
 };
 
 __device__ __forceinline__ long long gtime_ns() {
@@ -135,6 +136,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 __device__ __forceinline__ void epilogue_chunk_fast(const GemmParams& p, const uint32_t (&v)[32], const float4 (&bq)[8],
                                                     const float4 (&rq)[8], int b, int r, int n, int ks) {
   const long long row_off = (long long)b * p.out_bs + (long long)r * p.out_rs + (long long)ks * p.split_stride;
+  uint4 packed[4];  // bf16 output: the four 8-column groups, stored as two 32-byte pieces
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int ng = n + 8 * g;
@@ -160,15 +162,19 @@ __device__ __forceinline__ void epilogue_chunk_fast(const GemmParams& p, const u
     x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
     x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
     if (p.out_fp32) {
-      float* op = reinterpret_cast<float*>(p.out) + out_off;
-      *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
-      *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
+      // one 32-byte sector per lane per instruction (row strides are multiples of 8 elements, n of 32)
+      st_global_v8(reinterpret_cast<float*>(p.out) + out_off, make_float4(x[0], x[1], x[2], x[3]),
+                   make_float4(x[4], x[5], x[6], x[7]));
     } else {
-      uint4 o;
-      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&packed[g]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_off) = o;
+      bf16* op = reinterpret_cast<bf16*>(p.out) + out_off;
+      if (p.hm_T > 0 || (p.out_rs & 15)) {
+        *reinterpret_cast<uint4*>(op) = packed[g];  // head-major scatter / rows not 32-byte aligned: 16-byte pieces
+      } else if (g & 1) {
+        st_global_v8(op - 8, packed[g - 1], packed[g]);
+      }
     }
   }
 }
@@ -333,7 +339,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld32(taddr + c0, v);
           // request this chunk's bias and residual while the accumulator load is in flight
           const int nc = n0 + c0;
-          const bool fast = row_ok && nc + 32 <= p.N;
+          const bool fast = row_ok && nc + 32 <= p.N && p.v8ok;
           float4 bq[8], rq[8];
 #pragma unroll
           for (int g = 0; g < 8; ++g) { bq[g] = make_float4(0.f, 0.f, 0.f, 0.f); rq[g] = bq[g]; }
@@ -345,9 +351,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (p.residual) {
               const long long res_off = (long long)b * p.res_bs + (long long)r * p.res_rs + nc;
               if (p.res_fp32) {
-                const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + res_off);
+                const float* rp = reinterpret_cast<const float*>(p.residual) + res_off;
 #pragma unroll
-                for (int g = 0; g < 8; ++g) rq[g] = rp[g];
+                for (int g = 0; g < 8; g += 2) ld_global_v8(rp + 4 * g, rq[g], rq[g + 1]);
               } else {
                 const uint2* rp = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.residual) + res_off);
 #pragma unroll
@@ -543,6 +549,9 @@ void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   // ([splits][rows][out_row_stride]); the consumer (LayerNorm) adds the slabs in a fixed order, so
   // results do not depend on scheduling.  Bias / activation / residual are the consumer's job.
   p.trace = g_trace;
+  p.v8ok = (reinterpret_cast<uintptr_t>(d.out) & 31) == 0 && (d.split_stride % 8) == 0 &&
+           (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 31) == 0) && (d.out_batch_stride % 16) == 0 &&
+           (d.res_batch_stride % 8) == 0;
   p.splits = d.split_k > 1 ? d.split_k : 1;
   p.split_stride = d.split_stride;
   B200W_REQUIRE(p.splits == 1 || (d.out_fp32 && !d.bias && !d.residual && d.act == 0 && d.n_taps == 0 &&
