@@ -187,7 +187,6 @@ int b200w_conv1d_k3(const void* x_dev, const void* w_dev, const float* bias_dev,
 int b200w_enc_attention(const void* qkv_dev, int B, int T, int d, int n_heads, void* out_dev,
                         void* stream) {
   B200W_API_BEGIN
-  if (const char* kt = getenv("B200W_ENC_ATTN_KT")) enc_attention_set_block(atoi(kt));
   enc_attention(static_cast<const bf16*>(qkv_dev), B, T, d, n_heads, static_cast<bf16*>(out_dev),
                 static_cast<cudaStream_t>(stream));
   B200W_API_END

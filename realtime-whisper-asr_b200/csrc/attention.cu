@@ -1,13 +1,18 @@
 // Attention kernels.
-//  * enc_attn_kernel: non-causal flash-style self-attention for the encoder (T = 1500, head 64).
-//    S = Q K^T and O += P V run on tcgen05 with fp32 accumulators in TMEM; Q/K/V tiles arrive by
-//    TMA (128B swizzle) straight out of the fused QKV activation; the online softmax runs in
-//    registers (one query row per thread, exp2 domain) and hands P back through shared memory.
-//    Two CTAs per SM overlap each other's MMA and softmax phases.
-//  * dec_attn_kernel: decoder attention for few queries (decode steps, prompt prefill, the
-//    alignment pass): one warp per (query, head), keys/values gathered through the token-granular
-//    page table of the KV cache (self) or read densely from the per-chunk cross K/V.  Memory-bound
-//    CUDA-core work.  Optionally exports softmax probabilities of selected heads (alignment).
+//  * enc_attn_kernel: non-causal flash-style attention (head 64) on tcgen05: S = Q K^T and O += P V with
+//    fp32 accumulators in TMEM; Q/K/V tiles arrive by TMA (128B swizzle); the online softmax runs in
+//    registers (one query row per thread, exp2 domain) and hands P back through shared memory; three
+//    CTAs per SM overlap each other's MMA and softmax phases.  Two modes: encoder self-attention
+//    (T = 1500, operands = column ranges of the fused QKV activation) and cross attention for passes
+//    with many query rows per stream (prompts, the alignment pass): Q = activation rows of a segment,
+//    K/V = the per-chunk cross K/V blocks.
+//  * cross_attn_tc_kernel: decode-step cross attention, HBM-bound: K/V of every live (stream, head)
+//    stream once through a TMA ring, tcgen05 for both products, softmax pipelined into the loads.
+//  * cross_attn_kernel / cross_attn_split_kernel: CUDA-core cross attention; the first exports the
+//    probabilities of the alignment heads, the second is the fallback of the tensor-core kernel.
+//  * dec_attn_kernel: decoder self-attention over the token-granular paged KV cache: one CTA per
+//    (query, 4 heads), page-table row staged in shared memory, value rows prefetched to L2 during the
+//    key pass.  Latency-bound CUDA-core work.
 #include "attention.h"
 
 #include "gemm.h"
@@ -226,8 +231,6 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
-
-void enc_attention_set_block(int) {}  // kept for ABI stability: the block size is fixed at 64 keys
 
 template <int KT, int CTAS>
 static void launch_enc_attn(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out, cudaStream_t stream) {
@@ -561,147 +564,6 @@ __global__ void __launch_bounds__(XW * 32) cross_attn_kernel(const CrossAttnPara
       for (int w = 0; w < XW; ++w) sum += s_acc[(w * XQ + q) * HD + c];
       p.out[(long long)(q0 + q) * p.out_stride + h * HD + c] = __float2bfloat16(sum * s_inv[q]);
     }
-  }
-}
-
-// v2 (no probability export): every warp streams its own 32-key chunks with an online softmax and
-// the 16 partial results are merged at the end, so there is no CTA-wide phase barrier and every warp
-// keeps many independent loads in flight.  8 lanes share a key (8 dims each) for q.k; one lane per
-// 2 output dims for p.v.
-template <int NQ>
-__global__ void __launch_bounds__(XW * 32) cross_attn_stream_kernel(const CrossAttnParams p) {
-  extern __shared__ __align__(16) float xs2[];
-  float (*s_p)[NQ][32] = reinterpret_cast<float (*)[NQ][32]>(xs2);                       // [XW][NQ][32]
-  float (*s_o)[NQ][HD] = reinterpret_cast<float (*)[NQ][HD]>(xs2 + XW * NQ * 32);        // [XW][NQ][64]
-  float (*s_m)[NQ] = reinterpret_cast<float (*)[NQ]>(xs2 + XW * NQ * 32 + XW * NQ * HD);  // [XW][NQ]
-  float (*s_l)[NQ] = s_m + XW;
-  const int g = blockIdx.x, h = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = p.g_start[g], nq = p.g_count[g];
-  const long long base = p.kv_base_off[p.stream[q0]];
-  const bf16* kb = p.kbase + base + h * p.head_stride;
-  const bf16* vb = p.vbase + base + h * p.head_stride;
-  const int sub = lane & 7, kg = lane >> 3;  // 8 lanes per key, 4 keys per pass
-
-  float qr[NQ][8];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    if (q < nq) {
-      const uint4 u = *reinterpret_cast<const uint4*>(p.q + (long long)(q0 + q) * p.q_stride + h * HD + 8 * sub);
-      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __bfloat1622float2(u2[t]);
-        qr[q][2 * t] = f.x * p.scale;
-        qr[q][2 * t + 1] = f.y * p.scale;
-      }
-    } else {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) qr[q][t] = 0.f;
-    }
-  }
-  float m_run[NQ], l_run[NQ], acc[NQ][2];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) { m_run[q] = -INFINITY; l_run[q] = 0.f; acc[q][0] = acc[q][1] = 0.f; }
-
-  const int n_chunks = (p.len + 31) >> 5;
-  for (int ch = warp; ch < n_chunks; ch += XW) {
-    const int k0 = ch << 5;
-    // ---- q.k for 32 keys: 8 passes of 4 keys, all loads issued first
-    uint4 kv[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int key = k0 + it * 4 + kg;
-      kv[it] = key < p.len ? __ldg(reinterpret_cast<const uint4*>(kb + (long long)key * p.kv_row_stride + 8 * sub))
-                           : make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&kv[it]);
-      float kf[8];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __bfloat1622float2(u2[t]);
-        kf[2 * t] = f.x;
-        kf[2 * t + 1] = f.y;
-      }
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        float d = 0.f;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) d = fmaf(qr[q][t], kf[t], d);
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        d += __shfl_xor_sync(0xffffffffu, d, 2);
-        d += __shfl_xor_sync(0xffffffffu, d, 4);
-        if (sub == 0) s_p[warp][q][it * 4 + kg] = (k0 + it * 4 + kg) < p.len ? d : -INFINITY;
-      }
-    }
-    // V of the chunk (lane owns dims 2*lane, 2*lane+1): issued now, consumed after the softmax
-    uint32_t vv[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int key = k0 + i;
-      vv[i] = key < p.len ? __ldg(reinterpret_cast<const unsigned int*>(vb + (long long)key * p.kv_row_stride + 2 * lane))
-                          : 0u;
-    }
-    __syncwarp();
-    // ---- online softmax over the chunk (lane = key)
-    float alpha[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const float sv = s_p[warp][q][lane];
-      float mx = sv;
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float m_new = fmaxf(m_run[q], mx);
-      const float e = __expf(sv - m_new);
-      float sum = e;
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      alpha[q] = __expf(m_run[q] - m_new);
-      l_run[q] = l_run[q] * alpha[q] + sum;
-      m_run[q] = m_new;
-      s_p[warp][q][lane] = e;
-    }
-    __syncwarp();
-    // ---- p.v
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) { acc[q][0] *= alpha[q]; acc[q][1] *= alpha[q]; }
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float2 vf[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) vf[u] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[i + u]));
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const float4 pw = *reinterpret_cast<const float4*>(&s_p[warp][q][i]);
-        acc[q][0] = fmaf(pw.x, vf[0].x, acc[q][0]); acc[q][1] = fmaf(pw.x, vf[0].y, acc[q][1]);
-        acc[q][0] = fmaf(pw.y, vf[1].x, acc[q][0]); acc[q][1] = fmaf(pw.y, vf[1].y, acc[q][1]);
-        acc[q][0] = fmaf(pw.z, vf[2].x, acc[q][0]); acc[q][1] = fmaf(pw.z, vf[2].y, acc[q][1]);
-        acc[q][0] = fmaf(pw.w, vf[3].x, acc[q][0]); acc[q][1] = fmaf(pw.w, vf[3].y, acc[q][1]);
-      }
-    }
-    __syncwarp();
-  }
-  // ---- merge the 16 partial softmaxes
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    if (lane == 0) { s_m[warp][q] = m_run[q]; s_l[warp][q] = l_run[q]; }
-    *reinterpret_cast<float2*>(&s_o[warp][q][2 * lane]) = make_float2(acc[q][0], acc[q][1]);
-  }
-  __syncthreads();
-  for (int i = tid; i < NQ * HD; i += XW * 32) {
-    const int q = i >> 6, c = i & 63;
-    if (q >= nq) continue;
-    float M = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < XW; ++w) M = fmaxf(M, s_m[w][q]);
-    float L = 0.f, O = 0.f;
-#pragma unroll
-    for (int w = 0; w < XW; ++w) {
-      const float sc = __expf(s_m[w][q] - M);  // warps without keys: exp(-inf) = 0
-      L = fmaf(s_l[w][q], sc, L);
-      O = fmaf(s_o[w][q][c], sc, O);
-    }
-    p.out[(long long)(q0 + q) * p.out_stride + h * HD + c] = __float2bfloat16(O / L);
   }
 }
 

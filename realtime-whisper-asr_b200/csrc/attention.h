@@ -7,7 +7,6 @@ namespace b200w {
 // Encoder self-attention over the fused QKV activation: qkv bf16 [B][T][3d] (q | k | v, heads of
 // 64 inside each third) -> out bf16 [B][T][d].  softmax(q k^T / 8) v, non-causal.
 void enc_attention(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out, cudaStream_t stream);
-void enc_attention_set_block(int kt);  // keys per inner block: 64 (default, 3 CTAs/SM) or 128 (2 CTAs/SM)
 
 // Decoder attention for a handful of queries; one warp per (query, head).
 struct DecAttnParams {

@@ -752,7 +752,6 @@ int b200w_engine_finalize(b200w_engine* e) {
   B200W_CHECK_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   B200W_CHECK_CUDA(cudaEventCreateWithFlags(&e->join_event, cudaEventDisableTiming));
   e->use_graphs = getenv("B200W_NO_GRAPHS") == nullptr;
-  if (const char* kt = getenv("B200W_ENC_ATTN_KT")) enc_attention_set_block(atoi(kt));
   e->finalized = true;
   B200W_API_END
 }
