@@ -123,9 +123,9 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   for (int j = 0; j < nblk; ++j) {
     const uint32_t ph = j & 1;
-    if (tid == 0) {
-      if (j == 0) mbar_wait(barQ, 0);
-      mbar_wait(barK, ph);
+    if (tid == 0 && j == 0) {  // S of block 0; S of block j+1 is issued behind the P.V of block j (below)
+      mbar_wait(barQ, 0);
+      mbar_wait(barK, 0);
       tc_fence_after();
       const uint64_t qd = make_sw128_desc(smem_u32(sQ));
       const uint64_t kd = make_sw128_desc(smem_u32(sK));
@@ -192,6 +192,17 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_mma_bf16(tmem_O, pd, vd + 128 * k, idescO, k != 0);  // V: +16 key rows = +2048 B
       }
       tc_commit(barO);
+      if (j + 1 < nblk) {
+        // software pipeline: every thread is done with S of this block (barrier above), so the next block's
+        // S = Q K^T runs on the tensor pipe while the threads wait for / accumulate this block's O
+        mbar_wait(barK, ph ^ 1);
+        tc_fence_after();
+        const uint64_t qd = make_sw128_desc(smem_u32(sQ));
+        const uint64_t kd = make_sw128_desc(smem_u32(sK));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_S, qd + 2 * k, kd + 2 * k, idescS, k != 0);
+        tc_commit(barS);
+      }
     }
     mbar_wait(barO, ph);
     tc_fence_after();
