@@ -407,6 +407,139 @@ __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p
   *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
 }
 
+// Decode steps: the QKV projection arrives as split-K partial sums.  This kernel reduces the slabs of ITS
+// row and head group (bias, bf16 rounding: the same arithmetic as split_finalize), writes the new key /
+// value into the cache, and attends: the row's history comes from the cache through the page table, its
+// own position (the last one) from shared memory.  One launch instead of reduction + attention, and q
+// never goes through global memory.  A row only needs its own new key / value, so CTAs are independent.
+__global__ void __launch_bounds__(128) qkv_attn_kernel(const QkvAttnParams p) {
+  extern __shared__ float s_dyn[];  // [max_len] table (int) | [4][max_len] scores
+  __shared__ float s_q[256], s_k[256], s_v[256];
+  pdl_trigger();
+  const int qi = blockIdx.x, hg = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = hg * 256 + 2 * tid;  // this thread's two columns inside each of the q / k / v sections
+  const int d = p.d, N = 3 * d;
+  float2 bq = __ldg(reinterpret_cast<const float2*>(p.bias + c));
+  float2 bk = __ldg(reinterpret_cast<const float2*>(p.bias + d + c));
+  float2 bv = __ldg(reinterpret_cast<const float2*>(p.bias + 2 * d + c));
+  pdl_wait();
+  {
+    const float* pp = p.partial + (long long)qi * N + c;
+#pragma unroll 4
+    for (int s2 = 0; s2 < p.n_splits; ++s2) {
+      const float2 a = *reinterpret_cast<const float2*>(pp + s2 * p.split_stride);
+      const float2 b = *reinterpret_cast<const float2*>(pp + s2 * p.split_stride + d);
+      const float2 e = *reinterpret_cast<const float2*>(pp + s2 * p.split_stride + 2 * d);
+      bq.x += a.x; bq.y += a.y; bk.x += b.x; bk.y += b.y; bv.x += e.x; bv.y += e.y;
+    }
+  }
+  const __nv_bfloat162 q2 = __floats2bfloat162_rn(bq.x, bq.y), k2 = __floats2bfloat162_rn(bk.x, bk.y),
+                       v2 = __floats2bfloat162_rn(bv.x, bv.y);
+  const long long slot = p.slot[qi];
+  *reinterpret_cast<__nv_bfloat162*>(p.kpool + slot * d + c) = k2;
+  *reinterpret_cast<__nv_bfloat162*>(p.vpool + slot * d + c) = v2;
+  {
+    const float2 qf = __bfloat1622float2(q2), kf = __bfloat1622float2(k2), vf = __bfloat1622float2(v2);
+    s_q[2 * tid] = qf.x * p.scale; s_q[2 * tid + 1] = qf.y * p.scale;
+    s_k[2 * tid] = kf.x; s_k[2 * tid + 1] = kf.y;
+    s_v[2 * tid] = vf.x; s_v[2 * tid + 1] = vf.y;
+  }
+  int* s_tab = reinterpret_cast<int*>(s_dyn);
+  float* sc = s_dyn + p.max_len + warp * p.max_len;
+  const int len = p.kvlen[qi];
+  const int hist = len - 1;  // positions [0, hist) come from the cache, position hist is this row's own token
+  const int tr = p.trow[qi];
+  const int h = hg * 4 + warp;
+  const bf16* kb = p.kpool + h * HD;
+  const bf16* vb = p.vpool + h * HD;
+  {
+    const int* tab = p.table + (long long)tr * p.table_stride;
+    for (int i = tid; i < hist; i += 128) s_tab[i] = tab[i];
+  }
+  __syncthreads();
+  float q[HD];
+#pragma unroll
+  for (int i = 0; i < HD; ++i) q[i] = s_q[warp * HD + i];
+  float mx = -INFINITY;
+  for (int i = lane; i < hist; i += 32) {
+    const long long roff = (long long)s_tab[i] * d;
+    const bf16* kp = kb + roff;
+    uint4 kr[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) kr[cc] = __ldg(reinterpret_cast<const uint4*>(kp) + cc);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + roff));
+    float acc = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&kr[cc]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(u2[t]);
+        acc = fmaf(q[8 * cc + 2 * t], f.x, acc);
+        acc = fmaf(q[8 * cc + 2 * t + 1], f.y, acc);
+      }
+    }
+    sc[i] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  float own = 0.f;  // score of the row's own position (every lane computes it: smem broadcast reads)
+#pragma unroll
+  for (int i = 0; i < HD; ++i) own = fmaf(q[i], s_k[warp * HD + i], own);
+  mx = fmaxf(mx, own);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int i = lane; i < hist; i += 32) {
+    const float e = __expf(sc[i] - mx);
+    sc[i] = e;
+    sum += e;
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float p_own = __expf(own - mx);
+  sum += p_own;
+  const float inv = 1.0f / sum;
+  __syncwarp();
+  float2 acc = make_float2(p_own * s_v[warp * HD + 2 * lane], p_own * s_v[warp * HD + 2 * lane + 1]);
+  const bf16* vl = vb + 2 * lane;
+  int i = 0;
+  for (; i + 16 <= hist; i += 16) {
+    __nv_bfloat162 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)s_tab[i + u] * d);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const float pw = sc[i + u];
+      const float2 f = __bfloat1622float2(v[u]);
+      acc.x = fmaf(pw, f.x, acc.x);
+      acc.y = fmaf(pw, f.y, acc.y);
+    }
+  }
+  {
+    __nv_bfloat162 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      if (i + u < hist) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)s_tab[i + u] * d);
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      if (i + u < hist) {
+        const float2 f = __bfloat1622float2(v[u]);
+        acc.x = fmaf(sc[i + u], f.x, acc.x);
+        acc.y = fmaf(sc[i + u], f.y, acc.y);
+      }
+  }
+  bf16* op = p.out + (long long)qi * p.out_stride + h * HD + 2 * lane;
+  *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
+}
+
+void qkv_attention(const QkvAttnParams& p, int n_rows, int n_heads, cudaStream_t stream) {
+  if (n_rows <= 0) return;
+  B200W_REQUIRE(n_heads % 4 == 0 && p.d == n_heads * HD, "qkv_attention: heads must be a multiple of 4, head dim 64");
+  const size_t smem = (size_t)(1 + 4) * p.max_len * sizeof(float);
+  launch_pdl(qkv_attn_kernel, dim3(n_rows, n_heads / 4), dim3(128), smem, stream, p);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
 void dec_attention(const DecAttnParams& p, int n_heads, cudaStream_t stream) {
   if (p.n_queries <= 0) return;
   B200W_REQUIRE(n_heads % 2 == 0, "head count must be even");

@@ -31,6 +31,27 @@ struct DecAttnParams {
 };
 void dec_attention(const DecAttnParams& p, int n_heads, cudaStream_t stream);
 
+// Decode steps: split-K QKV partial sums -> (bias, bf16) -> new K/V into the cache + self-attention of the row.
+struct QkvAttnParams {
+  const float* partial = nullptr;  // [n_splits][rows][3d] fp32 slabs
+  int n_splits = 0;
+  long long split_stride = 0;
+  const float* bias = nullptr;     // [3d]
+  int d = 0;
+  const int* slot = nullptr;       // [rows] cache slot of the row's own token
+  bf16* kpool = nullptr;           // this layer's pools [slots][d]
+  bf16* vpool = nullptr;
+  const int* table = nullptr;      // [table rows][table_stride] position -> slot
+  int table_stride = 0;
+  const int* trow = nullptr;       // [rows]
+  const int* kvlen = nullptr;      // [rows] visible keys including the row's own position
+  bf16* out = nullptr;
+  int out_stride = 0;
+  float scale = 0.125f;
+  int max_len = 0;
+};
+void qkv_attention(const QkvAttnParams& p, int n_rows, int n_heads, cudaStream_t stream);
+
 // Cross attention for the decoder: groups of up to 8 consecutive query rows of the SAME stream
 // (beams of one chunk, or consecutive prompt / teacher-forced tokens) share one pass over that
 // stream's K/V.  K/V of position t, head h: kbase/vbase + kv_base_off[stream] + h * head_stride + t * kv_row_stride.

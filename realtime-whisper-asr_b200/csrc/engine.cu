@@ -479,12 +479,24 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     RUN(1) { OP(1); layernorm(x, nullptr, L.ln1.g, L.ln1.b, h, n, d, s, &pend); }
     // decode steps only: the choice must not depend on how many streams are batched (batch invariance)
     const bool sk = use_skinny() && e->step_pass && d % 128 == 0;
+    // reduction of the QKV slabs + cache write + self-attention in one kernel (needs heads % 4 == 0)
+    static const bool use_fused = getenv("B200W_NO_FUSED_ATTN") == nullptr;
+    const bool fused_attn = sk && use_fused && e->H % 4 == 0 && !((ablate_mask() >> 2) & 1u);
     if (sk) {
       // split-K QKV projection; the reduction adds the bias, rounds to bf16 and scatters K / V into the cache
       RUN(2) {
         OP(2);
         const SplitReduce r = skinny_split(e, h, n, d, L.qkv, 3 * d, 4, s);
-        split_finalize(r.partial, r.n, r.stride, r.bias, n, 3 * d, 0, qkv, 3 * d, m.slot, kp, vp, d, s);
+        if (fused_attn) {
+          QkvAttnParams qa;
+          qa.partial = r.partial; qa.n_splits = r.n; qa.split_stride = r.stride; qa.bias = r.bias; qa.d = d;
+          qa.slot = m.slot; qa.kpool = kp; qa.vpool = vp;
+          qa.table = table; qa.table_stride = e->Tctx; qa.trow = m.trow; qa.kvlen = m.kvlen;
+          qa.out = attn; qa.out_stride = d; qa.scale = 0.125f; qa.max_len = max_kvlen;
+          qkv_attention(qa, n, e->H, s);
+        } else {
+          split_finalize(r.partial, r.n, r.stride, r.bias, n, 3 * d, 0, qkv, 3 * d, m.slot, kp, vp, d, s);
+        }
       }
     } else {
       RUN(2) { OP(2); linear(h, n, d, L.qkv, 3 * d, qkv, 3 * d, 0, 0, nullptr, 0, 0, s); }
@@ -495,7 +507,7 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     a.kbase = kp; a.vbase = vp; a.kv_row_stride = d;
     a.table = table; a.table_stride = e->Tctx; a.trow = m.trow; a.kvlen = m.kvlen;
     a.out = attn; a.out_stride = d; a.scale = 0.125f; a.n_queries = n; a.max_len = max_kvlen;
-    RUN(4) { OP(4); dec_attention(a, e->H, s); }
+    if (!fused_attn) RUN(4) { OP(4); dec_attention(a, e->H, s); }
     RUN(5) { OP(5); pend = residual_linear(e, attn, n, d, L.out, x, s); }
     // cross attention
     RUN(1) { OP(1); layernorm(x, nullptr, L.ln2.g, L.ln2.b, h, n, d, s, &pend); }
