@@ -47,6 +47,11 @@ int b200w_gemm_set_trace(void* dev_buf);
  * launches and algorithmic work (bytes for op 7 = decode cross attention; 0 where not tracked). */
 int b200w_op_profile_enable(int on);
 int b200w_op_profile_read(int op, const char** name, double* total_ms, int64_t* launches, double* work);
+/* Step probe (always on): CUDA events around the decode cross attention of the middle decoder layer in every decode
+ * step, recorded INSIDE the captured step graph (external event nodes).  Totals since the last reset: elapsed ms,
+ * launches, algorithmic bytes (K and V of every live (stream, head) once). */
+int b200w_step_probe_reset(void);
+int b200w_step_probe_read(double* total_ms, int64_t* launches, double* bytes);
 int b200w_gemm_profile_begin(int bn);
 int b200w_gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches);
 

@@ -45,6 +45,8 @@ SIGNATURES = {
     "b200w_gemm_set_trace": (_i, [_vp]),
     "b200w_op_profile_enable": (_i, [_i]),
     "b200w_op_profile_read": (_i, [_i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "b200w_step_probe_reset": (_i, []),
+    "b200w_step_probe_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "b200w_gemm_profile_begin": (_i, [_i]),
     "b200w_gemm_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "b200w_logmel": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),

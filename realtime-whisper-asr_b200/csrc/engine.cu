@@ -148,6 +148,9 @@ struct b200w_engine {
   unsigned long long launches_per_step = 0;
   cudaStream_t own_stream = nullptr;  // decode runs here (the legacy default stream cannot be captured)
   cudaEvent_t join_event = nullptr;
+  // in-graph probe: events around the decode cross attention of one layer, every decode step (bench roofline)
+  cudaEvent_t xev0 = nullptr, xev1 = nullptr;
+  bool xev_recorded = false;
 };
 
 namespace {
@@ -260,6 +263,17 @@ struct OpScope {
   }
 };
 #define OP(id) OpScope _op_scope_##id(id, s)
+// Step probe: CUDA events around the tensor-core cross attention of ONE decoder layer in every decode step --
+// inside the captured step graph as external event-record nodes -- so that bench.py can time the dominant
+// kernel inside its timed region (a graph replay cannot be bracketed from outside).  Totals since the last reset.
+static double g_probe_ms = 0, g_probe_bytes = 0;
+static long long g_probe_n = 0;
+static void probe_record(cudaEvent_t ev, cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  B200W_CHECK_CUDA(cudaStreamIsCapturing(s, &st));
+  if (st == cudaStreamCaptureStatusActive) B200W_CHECK_CUDA(cudaEventRecordWithFlags(ev, s, cudaEventRecordExternal));
+  else B200W_CHECK_CUDA(cudaEventRecord(ev, s));
+}
 // Development aid: B200W_ABLATE=<bit mask over the op ids above> drops those ops from the decoder pass
 // (results are garbage) so that an op's real cost inside the captured step can be read off the step time.
 static unsigned ablate_mask() {
@@ -558,8 +572,11 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
           cross_attention(c, m.n_groups, e->H, m.max_group, s, nullptr);
         }
       } else if (tc) {
+        const bool probe = step_tc && e->step_pass && l == e->Ld / 2 && !g_optimer.on;
+        if (probe) probe_record(e->xev0, s);
         cross_attention_tc(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, d, m.stream, m.g_start, m.g_count,
                            m.n_live, m.n_groups, attn, d, 0.125f, e->x_tc.p, s, e->step_pass ? 1 : 0);
+        if (probe) { probe_record(e->xev1, s); e->xev_recorded = true; }
         if (c.head_export) {
           c.export_only = 1;
           cross_attention(c, m.n_groups, e->H, m.max_group, s, nullptr);
@@ -655,6 +672,8 @@ int b200w_engine_destroy(b200w_engine* e) {
     for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.exec);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->join_event) cudaEventDestroy(e->join_event);
+    if (e->xev0) cudaEventDestroy(e->xev0);
+    if (e->xev1) cudaEventDestroy(e->xev1);
     delete e;
   }
   B200W_API_END
@@ -763,6 +782,8 @@ int b200w_engine_finalize(b200w_engine* e) {
                                    (size_t)Bm * 128 * 4}));
   B200W_CHECK_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   B200W_CHECK_CUDA(cudaEventCreateWithFlags(&e->join_event, cudaEventDisableTiming));
+  B200W_CHECK_CUDA(cudaEventCreate(&e->xev0));
+  B200W_CHECK_CUDA(cudaEventCreate(&e->xev1));
   e->use_graphs = getenv("B200W_NO_GRAPHS") == nullptr;
   e->finalized = true;
   B200W_API_END
@@ -894,6 +915,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     B200W_CHECK_CUDA(cudaStreamSynchronize(s));  // mk goes out of scope
   }
 
+  e->xev_recorded = false;
   const bool timing = getenv("B200W_DECODE_TIMING") != nullptr;
   g_optimer.on = g_optimer.forced || (getenv("B200W_DECODE_PROFILE") != nullptr && !e->use_graphs);
   auto now = [] { return std::chrono::steady_clock::now(); };
@@ -1096,6 +1118,16 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     cur ^= 1;
     B200W_CHECK_CUDA(cudaStreamSynchronize(s));
     t_gpu += ms_since(t_s1);
+    if (e->xev_recorded) {  // the probe events were (re)recorded by this step: graph replay or eager launch
+      float pms = 0.f;
+      if (cudaEventElapsedTime(&pms, e->xev0, e->xev1) == cudaSuccess) {
+        g_probe_ms += pms;
+        g_probe_n += 1;
+        g_probe_bytes += (double)pm.n_live_host * e->H * 2.0 * e->Tenc * HEAD_DIM * 2.0;
+      } else {
+        cudaGetLastError();
+      }
+    }
     if (ablate_mask() != 0)  // timing-only runs: keep every beam alive whatever the (garbage) logits say
       for (int r = 0; r < B * K; ++r)
         for (int c = 0; c < k_top; ++c) { h_ids[r * k_top + c] = 1000 + c; h_lp[r * k_top + c] = -1.f - c; }
@@ -1359,5 +1391,18 @@ extern "C" int b200w_op_profile_read(int op, const char** name, double* total_ms
   if (total_ms) *total_ms = g_optimer.tot_ms[op];
   if (launches) *launches = g_optimer.tot_n[op];
   if (work) *work = g_optimer.tot_work[op];
+  return 0;
+}
+
+extern "C" int b200w_step_probe_reset(void) {
+  g_probe_ms = 0;
+  g_probe_bytes = 0;
+  g_probe_n = 0;
+  return 0;
+}
+extern "C" int b200w_step_probe_read(double* total_ms, int64_t* launches, double* bytes) {
+  if (total_ms) *total_ms = g_probe_ms;
+  if (launches) *launches = g_probe_n;
+  if (bytes) *bytes = g_probe_bytes;
   return 0;
 }
