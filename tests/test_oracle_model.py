@@ -112,3 +112,41 @@ def test_align_path_is_monotone(hf_pair):
     ti, fi, tp = OA.align(orc, enc[0], [1101, 5, 6], 1103, 1100, [20, 21, 22, 23], 600, [(1, 0), (1, 1)])
     assert ti[0] == 0 and fi[0] == 0 and ti[-1] == 4 and fi[-1] == 299
     assert np.all(np.diff(ti) >= 0) and np.all(np.diff(fi) >= 0) and len(tp) == 4 and np.all((tp >= 0) & (tp <= 1))
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_greedy_decode_matches_transformers_loop(hf_pair, seed):
+    """Greedy decoding with Whisper's logit rules: the oracle's decode_one against a hand loop over transformers'
+    model + transformers' own logits processors (suppress lists, begin-suppress, timestamp rules) + argmax."""
+    from types import SimpleNamespace
+
+    from transformers.generation.logits_process import (SuppressTokensAtBeginLogitsProcessor,
+                                                        SuppressTokensLogitsProcessor,
+                                                        WhisperTimeStampLogitsProcessor)
+    hf, orc = hf_pair
+    torch.manual_seed(seed)
+    mel = torch.randn(1, 80, 3000)
+    o = _opts(max_new_tokens=14)
+    prompt = [1101, 5, 6]
+    with torch.no_grad():
+        enc = orc.encode(mel)
+        got = OD.decode_one(orc, enc[0], prompt, o).tokens
+        cfg = SimpleNamespace(no_timestamps_token_id=o.no_timestamps, eos_token_id=o.eot, bos_token_id=o.eot,
+                              max_initial_timestamp_index=o.max_initial_timestamp_index,
+                              _detect_timestamp_from_logprob=True)
+        procs = [SuppressTokensLogitsProcessor(list(o.suppress_ids)),
+                 SuppressTokensAtBeginLogitsProcessor(list(o.blank_ids), begin_index=len(prompt)),
+                 WhisperTimeStampLogitsProcessor(cfg, begin_index=len(prompt))]
+        enc_hf = hf.model.encoder(mel).last_hidden_state
+        ids = list(prompt)
+        ref = []
+        for _ in range(14):
+            logits = hf(encoder_outputs=(enc_hf,), decoder_input_ids=torch.tensor([ids])).logits[:, -1, :]
+            for p in procs:
+                logits = p(torch.tensor([ids]), logits)
+            t = int(torch.argmax(logits, dim=-1))
+            if t == o.eot:
+                break
+            ids.append(t)
+            ref.append(t)
+    assert got == ref
