@@ -150,3 +150,18 @@ def test_greedy_decode_matches_transformers_loop(hf_pair, seed):
             ids.append(t)
             ref.append(t)
     assert got == ref
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_dtw_and_median_match_transformers(seed):
+    """Word-timing building blocks against transformers' restatement of OpenAI's timing.py: same DTW path (tie
+    breaking included) and the same reflect-padded median filter on random matrices."""
+    g = pytest.importorskip("transformers.models.whisper.generation_whisper")
+    rng = np.random.default_rng(seed)
+    m = rng.normal(size=(17 + seed, 140)).astype(np.float32)
+    m[3] = m[4]  # exact ties along a row pair
+    ti, fi = OA.dtw(-m)
+    rti, rfi = g._dynamic_time_warping(-m)
+    assert np.array_equal(ti, rti) and np.array_equal(fi, rfi)
+    w = rng.normal(size=(3, 9, 75)).astype(np.float32)
+    assert np.array_equal(OA.median_filter(w, 7), g._median_filter(torch.from_numpy(w), 7).numpy())
