@@ -310,7 +310,7 @@ def run_b200(args, rank, world, local):
     launches0 = _lib.launch_count()
     import ctypes as C
     _lib.check(lib.b200w_gemm_profile_begin(256))
-    _lib.check(lib.b200w_step_probe_reset())
+    _lib.check(lib.b200w_step_probe_reset(model.engine._h))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -318,7 +318,7 @@ def run_b200(args, rank, world, local):
     ev1.record()
     barrier()
     pr_ms, pr_n, pr_bytes = C.c_double(), C.c_int64(), C.c_double()
-    _lib.check(lib.b200w_step_probe_read(C.byref(pr_ms), C.byref(pr_n), C.byref(pr_bytes)))
+    _lib.check(lib.b200w_step_probe_read(model.engine._h, C.byref(pr_ms), C.byref(pr_n), C.byref(pr_bytes)))
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = _lib.launch_count() - launches0
     tms, tfl, tn = C.c_double(), C.c_double(), C.c_int64()
@@ -379,14 +379,14 @@ def run_b200(args, rank, world, local):
                      "share_of_step": tms.value / dev_ms if dev_ms else None,
                      "timing": "CUDA events around every launch inside the timed region"}
     # ---- decode ops: one extra pass of the same step, decode steps launched eagerly with events per op
-    _lib.check(lib.b200w_op_profile_enable(1))
+    _lib.check(lib.b200w_op_profile_enable(model.engine._h, 1))
     model.transcribe_batch(None, device_audio=(audio_dev, offsets), **kw)
     torch.cuda.synchronize()
-    _lib.check(lib.b200w_op_profile_enable(0))
+    _lib.check(lib.b200w_op_profile_enable(model.engine._h, 0))
     ops = {}
     for op in range(16):
         nm, ms_, n_, wk_ = C.c_char_p(), C.c_double(), C.c_int64(), C.c_double()
-        _lib.check(lib.b200w_op_profile_read(op, C.byref(nm), C.byref(ms_), C.byref(n_), C.byref(wk_)))
+        _lib.check(lib.b200w_op_profile_read(model.engine._h, op, C.byref(nm), C.byref(ms_), C.byref(n_), C.byref(wk_)))
         if n_.value:
             ops[nm.value.decode()] = {"ms": ms_.value, "launches": int(n_.value), "work": wk_.value}
     hbm_peak = peaks.get("hbm_gbs") or 6650.0

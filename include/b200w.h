@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200W_ABI_VERSION 1
+#define B200W_ABI_VERSION 2
 
 const char* b200w_last_error(void);
 int b200w_abi_version(void);
@@ -45,13 +45,15 @@ int b200w_gemm_set_trace(void* dev_buf);
  * decode steps are launched eagerly (no CUDA graph) with CUDA events around every op on the launching
  * stream; totals accumulate per op id until the next enable(1).  read(): op 0..15 -> name, total ms,
  * launches and algorithmic work (bytes for op 7 = decode cross attention; 0 where not tracked). */
-int b200w_op_profile_enable(int on);
-int b200w_op_profile_read(int op, const char** name, double* total_ms, int64_t* launches, double* work);
+struct b200w_engine;
+int b200w_op_profile_enable(struct b200w_engine* e, int on);
+int b200w_op_profile_read(struct b200w_engine* e, int op, const char** name, double* total_ms, int64_t* launches,
+                          double* work);
 /* Step probe (always on): CUDA events around the decode cross attention of the middle decoder layer in every decode
  * step, recorded INSIDE the captured step graph (external event nodes).  Totals since the last reset: elapsed ms,
  * launches, algorithmic bytes (K and V of every live (stream, head) once). */
-int b200w_step_probe_reset(void);
-int b200w_step_probe_read(double* total_ms, int64_t* launches, double* bytes);
+int b200w_step_probe_reset(struct b200w_engine* e);
+int b200w_step_probe_read(struct b200w_engine* e, double* total_ms, int64_t* launches, double* bytes);
 int b200w_gemm_profile_begin(int bn);
 int b200w_gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches);
 
@@ -106,12 +108,14 @@ int b200w_skinny_gemm(const void* X_dev, const void* W_dev, const float* bias_de
  *   cross_kv_dev  bf16 [n_streams][n_layers][k|v][n_heads][len][64]       q_dev  bf16 [rows][n_heads*64]
  *   stream_dev    int32 [rows] stream of each row       g_start_dev / g_count_dev  int32 [n_groups]
  *   n_live_dev    int32 [1]: groups [0, n_live) are processed             out_dev bf16 [rows][n_heads*64]
- *   scratch_dev   b200w_cross_attention_tc_scratch_bytes() bytes, zeroed once by the caller */
+ *   scratch_dev   b200w_cross_attention_tc_scratch_bytes() bytes, zeroed once by the caller
+ *   pieces        key ranges every (group, head) item is cut into (a divisor of ceil(len/128), else 1 is used):
+ *                 a function of the shapes only, so a stream's result never depends on its batch neighbours */
 int64_t b200w_cross_attention_tc_scratch_bytes(void);
 int b200w_cross_attention_tc(const void* cross_kv_dev, int n_streams, int n_layers, int layer, int n_heads, int len,
                              const void* q_dev, const int32_t* stream_dev, const int32_t* g_start_dev,
                              const int32_t* g_count_dev, const int32_t* n_live_dev, int n_groups, void* out_dev,
-                             float scale, void* scratch_dev, void* stream);
+                             float scale, void* scratch_dev, int pieces, void* stream);
 
 /* Cross attention for passes with many query rows per stream (prompts, alignment): flash kernel, one CTA per
  * (128 query rows of a segment, head).  Segments = runs of consecutive query rows of one stream.

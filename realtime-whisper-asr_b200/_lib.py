@@ -43,10 +43,10 @@ SIGNATURES = {
     "b200w_abi_version": (_i, []),
     "b200w_launch_count": (C.c_uint64, []),
     "b200w_gemm_set_trace": (_i, [_vp]),
-    "b200w_op_profile_enable": (_i, [_i]),
-    "b200w_op_profile_read": (_i, [_i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
-    "b200w_step_probe_reset": (_i, []),
-    "b200w_step_probe_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "b200w_op_profile_enable": (_i, [_vp, _i]),
+    "b200w_op_profile_read": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "b200w_step_probe_reset": (_i, [_vp]),
+    "b200w_step_probe_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "b200w_gemm_profile_begin": (_i, [_i]),
     "b200w_gemm_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "b200w_logmel": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
@@ -55,7 +55,7 @@ SIGNATURES = {
     "b200w_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _vp]),
     "b200w_skinny_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _vp]),
     "b200w_cross_attention_tc_scratch_bytes": (C.c_int64, []),
-    "b200w_cross_attention_tc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _f, _vp, _vp]),
+    "b200w_cross_attention_tc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _f, _vp, _i, _vp]),
     "b200w_cross_attention_flash": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "b200w_conv1d_k3": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200w_enc_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
@@ -89,7 +89,7 @@ def load(path: str | None = None):
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.b200w_abi_version() != 1:
+    if lib.b200w_abi_version() != 2:
         raise B200WError("libb200whisper.so ABI version mismatch")
     _lib = lib
     return lib

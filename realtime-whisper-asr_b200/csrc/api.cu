@@ -4,6 +4,10 @@
 
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "attention.h"
 #include "common.h"
 #include "frontend.h"
@@ -12,7 +16,7 @@
 
 namespace b200w {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& s) { t_last_error = s; }
@@ -24,13 +28,29 @@ bool pdl_enabled() {
 }
 
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];  // per device ordinal; 0 = not read yet
+  int dev = 0;
+  B200W_CHECK_CUDA(cudaGetDevice(&dev));
+  const int slot = dev & 63;
+  int n = cache[slot].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    B200W_CHECK_CUDA(cudaGetDevice(&dev));
     B200W_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    cache[slot].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+void ensure_dynamic_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;
+  int dev = 0;
+  B200W_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = done[{dev, func}];
+  if (bytes > have) {
+    B200W_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
 }
 
 }  // namespace b200w
@@ -41,7 +61,7 @@ extern "C" {
 
 const char* b200w_last_error(void) { return get_last_error(); }
 int b200w_abi_version(void) { return B200W_ABI_VERSION; }
-uint64_t b200w_launch_count(void) { return g_launch_count; }
+uint64_t b200w_launch_count(void) { return g_launch_count.load(); }
 
 int b200w_gemm_set_trace(void* dev_buf) {
   if (getenv("B200W_TRACE_CROSS")) cross_tc_set_trace(dev_buf);
@@ -150,17 +170,17 @@ int b200w_skinny_gemm(const void* X_dev, const void* W_dev, const float* bias_de
   B200W_API_END
 }
 
-int64_t b200w_cross_attention_tc_scratch_bytes(void) { return (int64_t)cross_attention_tc_scratch_bytes() + 256; }
+int64_t b200w_cross_attention_tc_scratch_bytes(void) { return (int64_t)cross_attention_tc_scratch_bytes(); }
 
 int b200w_cross_attention_tc(const void* cross_kv_dev, int n_streams, int n_layers, int layer, int n_heads, int len,
                              const void* q_dev, const int32_t* stream_dev, const int32_t* g_start_dev,
                              const int32_t* g_count_dev, const int32_t* n_live_dev, int n_groups, void* out_dev,
-                             float scale, void* scratch_dev, void* stream) {
+                             float scale, void* scratch_dev, int pieces, void* stream) {
   B200W_API_BEGIN
   cross_attention_tc(static_cast<const bf16*>(cross_kv_dev), n_streams, n_layers, layer, n_heads, len,
                      static_cast<const bf16*>(q_dev), n_heads * 64, stream_dev, g_start_dev, g_count_dev, n_live_dev,
                      n_groups, static_cast<bf16*>(out_dev), n_heads * 64, scale, scratch_dev,
-                     static_cast<cudaStream_t>(stream));
+                     static_cast<cudaStream_t>(stream), pieces);
   B200W_API_END
 }
 

@@ -249,12 +249,7 @@ static void launch_enc_attn(const bf16* qkv, int B, int T, int d, int n_heads, b
   make_tmap_bf16_3d(&tmQ, qkv, 3 * (uint64_t)d, T, B, 3 * (uint64_t)d, (uint64_t)T * 3 * d, HD, 128);
   make_tmap_bf16_3d(&tmKV, qkv, 3 * (uint64_t)d, T, B, 3 * (uint64_t)d, (uint64_t)T * 3 * d, HD, KT);
   constexpr int smem_bytes = TILE_BYTES + 2 * KT * HD * 2 + 128 * KT * 2 + 5 * 8 + 16 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200W_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_kernel<KT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          smem_bytes));
-    configured = true;
-  }
+  ensure_dynamic_smem(enc_attn_kernel<KT, CTAS>, smem_bytes);
   EncAttnParams p{T, d, 0.125f * 1.4426950408889634f, out, nullptr, nullptr, nullptr, 0, 0, n_heads};
   enc_attn_kernel<KT, CTAS><<<dim3(cdiv(T, QT), n_heads, B), 128, smem_bytes, stream>>>(tmQ, tmKV, p);
   B200W_COUNT_LAUNCH();
@@ -279,11 +274,7 @@ void cross_attention_flash(const bf16* cross_kv, int n_streams, int n_layers, in
   make_tmap_bf16_3d(&tmQ, q, d, n_q_rows, 1, d, (uint64_t)n_q_rows * d, HD, 128);
   make_tmap_bf16_3d(&tmKV, cross_kv, HD, len, (uint64_t)n_streams * n_layers * 2 * n_heads, HD, (uint64_t)len * HD, HD, 64);
   constexpr int smem_bytes = TILE_BYTES + 2 * 64 * HD * 2 + 128 * 64 * 2 + 5 * 8 + 16 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200W_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = true;
-  }
+  ensure_dynamic_smem(enc_attn_kernel<64, 3>, smem_bytes);
   EncAttnParams p{len, d, 0.125f * 1.4426950408889634f, out, seg_start, seg_count, row_stream,
                   n_layers * 2 * n_heads, 2 * layer * n_heads, n_heads};
   launch_pdl(enc_attn_kernel<64, 3>, dim3(cdiv(max_seg_rows, QT), n_heads, n_segs), dim3(128), (size_t)smem_bytes, stream,
@@ -885,10 +876,11 @@ static void launch_cross_split(const CrossAttnParams& p, int n_groups, int n_hea
 //   O[128 x 64]   += P[128 x 128 keys] . V_tile[128 keys x 64]   (rows >= 8 of P are don't-care: a
 //   row of A only feeds the same row of D, so the operand tile may overlap unrelated shared memory)
 // Warps 0-3: Q staging, softmax, output.  Warp 4: TMA producer.  Warp 5: MMA issuer.
-// Load balance: with I items on G CTAs, floor(I/G) rounds of whole items are followed by one round
-// in which each of the remaining r items is cut into s <= G/r key ranges (s divides the tile count);
-// the pieces leave un-normalised partial results in global scratch and the last piece to finish
-// (atomic counter, self-resetting) merges them.  640 items on 148 SMs: 4 + 1/3 rounds instead of 5.
+// Load balance and batch invariance: every item is ALWAYS cut into the same `pieces` key ranges (a divisor of
+// the tile count, chosen by the caller from the shapes alone), the units (item, piece) are numbered item-major
+// and dealt to the CTAs in contiguous runs.  A piece leaves an un-normalised partial result in global scratch
+// and the last piece of an item to finish (atomic counter, self-resetting) merges them in piece order, so an
+// item's arithmetic never depends on how many other items share the launch.  pieces = 1: items are computed whole.
 static constexpr int XT_RING = 5;    // 16 KB slots; two CTAs share an SM and cover each other's softmax phases
 static constexpr int XT_MAX_TILES = 12;  // keys <= 1536
 static constexpr int XT_P_BYTES = XT_MAX_TILES * 2 * 1024;
@@ -913,9 +905,9 @@ struct CrossTcParams {
   bf16* out;
   int out_stride;
   float scale_log2e;
-  int allow_split;  // 0: every item is computed whole (results do not depend on how many items share the launch)
-  float* partial;  // [grid][XT_MAX_PIECES][XT_PART_FLOATS]
-  int* counters;   // [grid], zero between launches
+  int pieces;      // key ranges per item (divides the tile count; 1 = whole items)
+  float* partial;  // [item][XT_MAX_PIECES][XT_PART_FLOATS]
+  int* counters;   // [item], zero between launches
   long long* trace;  // development aid: [cta][unit < 6][8] clock64 stamps, or null
 };
 #define XT_TRACE(slot) do { if (p.trace && it < 6) p.trace[(blockIdx.x * 6 + it) * 8 + (slot)] = clock64(); } while (0)
@@ -923,25 +915,17 @@ struct CrossTcParams {
 struct XtUnit {
   int item, t0, t1, piece, n_pieces, tail_idx;
 };
-// u-th unit of this CTA (every role evaluates the same sequence)
-__device__ __forceinline__ bool xt_unit(int u, int n_items, int n_tiles, XtUnit& un, int allow_split = 1) {
-  const int G = gridDim.x, R = n_items / G, r = n_items - R * G;
-  if (u < R) {
-    un.item = blockIdx.x + u * G;
-    un.t0 = 0; un.t1 = n_tiles; un.piece = 0; un.n_pieces = 1; un.tail_idx = 0;
-    return true;
-  }
-  if (u > R || r == 0) return false;
-  int s = 1;
-  if (allow_split)
-    for (int d = 2; d <= XT_MAX_PIECES; ++d)
-      if (n_tiles % d == 0 && d * r <= G) s = d;
-  if ((int)blockIdx.x >= r * s) return false;
-  un.tail_idx = blockIdx.x / s;
-  un.piece = blockIdx.x - un.tail_idx * s;
-  un.n_pieces = s;
-  un.item = R * G + un.tail_idx;
-  const int tpp = n_tiles / s;
+// u-th unit of this CTA (every role evaluates the same sequence): CTA c owns the units [n c / G, n (c+1) / G)
+__device__ __forceinline__ bool xt_unit(int u, int n_items, int n_tiles, XtUnit& un, int pieces) {
+  const long long n_units = (long long)n_items * pieces;
+  const int lo = (int)(n_units * blockIdx.x / gridDim.x), hi = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
+  const int g = lo + u;
+  if (g >= hi) return false;
+  un.item = g / pieces;
+  un.piece = g - un.item * pieces;
+  un.n_pieces = pieces;
+  un.tail_idx = un.item;
+  const int tpp = n_tiles / pieces;
   un.t0 = un.piece * tpp;
   un.t1 = un.t0 + tpp;
   return true;
@@ -1041,7 +1025,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
   if (warp == 4) {
     if (lane == 0) {  // ---------------- TMA producer: K tiles then V tiles of every unit
       uint32_t slot = 0, phase = 0;
-      for (int u = 0; xt_unit(u, n_items, n_tiles, un, p.allow_split); ++u) {
+      for (int u = 0; xt_unit(u, n_items, n_tiles, un, p.pieces); ++u) {
         const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
         const int blk = p.stream[p.g_start[g]] * p.blocks_per_stream + p.layer_block0 + h;
         for (int kv = 0; kv < 2; ++kv)
@@ -1055,7 +1039,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
       }
     } else {  // ---------------- lanes 1..31: stage the Q tile of unit `it` one unit ahead of its use
       pdl_wait();
-      for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.allow_split); ++it) {
+      for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.pieces); ++it) {
         const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
         const int q0 = p.g_start[g], nq = p.g_count[g];
         uint4 u[5];
@@ -1068,7 +1052,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
             u[r] = *reinterpret_cast<const uint4*>(p.q + (long long)(q0 + qr) * p.q_stride + h * HD + 8 * ch);
         }
         // buffer it&1 was last read by the QK MMAs of unit it-2: its last score barrier tells when they are done
-        if (it >= 2) mbar_wait(bar_s0 + 8 * (n_tiles - 1), (uint32_t)(it & 1));  // unit it-2 is a whole item
+        if (it >= 2) mbar_wait(bar_s0 + 8 * (n_tiles / p.pieces - 1), (uint32_t)(it & 1));  // every unit has the same tile count
         uint8_t* dst = sQ + (it & 1) * XT_Q_BYTES;
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
@@ -1085,7 +1069,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
       constexpr uint32_t idescS = make_idesc_bf16(128, 16, 0, 0);  // K (K-major) x Q (K-major)
       constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);  // P (K-major) x V (MN-major)
       uint32_t slot = 0, phase = 0;
-      for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.allow_split); ++it) {
+      for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.pieces); ++it) {
         const int nt = un.t1 - un.t0;
         const uint32_t par = it & 1;
         mbar_wait(bar_q0 + 8 * par, (uint32_t)((it >> 1) & 1));
@@ -1121,7 +1105,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
   } else {  // ---------------- warps 0..3: softmax (thread = key row of every tile) and output
     pdl_wait();
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.allow_split); ++it) {
+    for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.pieces); ++it) {
       const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
       const int q0 = p.g_start[g], nq = p.g_count[g];
       const int nt = un.t1 - un.t0;
@@ -1268,37 +1252,37 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
 static long long* g_xt_trace = nullptr;
 void cross_tc_set_trace(void* dev_buf) { g_xt_trace = static_cast<long long*>(dev_buf); }
 
+static constexpr int XT_MAX_ITEMS = 64 * 32;  // (live group, head) items per launch: <= 64 groups, <= 32 heads
 size_t cross_attention_tc_scratch_bytes() {
-  return (size_t)XT_CTAS_PER_SM * num_sms() * (XT_MAX_PIECES * XT_PART_FLOATS * sizeof(float) + sizeof(int));
+  return (size_t)XT_MAX_ITEMS * (XT_MAX_PIECES * XT_PART_FLOATS * sizeof(float) + sizeof(int)) + 256;
 }
 
 void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int layer, int n_heads, int len,
                         const bf16* q, int q_stride, const int* stream, const int* g_start, const int* g_count,
                         const int* n_live_groups, int n_groups, bf16* out, int out_stride, float scale, void* scratch,
-                        cudaStream_t cs, int allow_split) {
+                        cudaStream_t cs, int pieces) {
   if (n_groups <= 0) return;
   B200W_REQUIRE(len <= 128 * XT_MAX_TILES, "cross_attention_tc: at most 1536 keys");
   CUtensorMap tm;
   make_tmap_bf16_3d(&tm, cross_kv, HD, len, (uint64_t)n_streams * n_layers * 2 * n_heads, HD, (uint64_t)len * HD, HD,
                     128);
-  static bool configured = false;
-  if (!configured) {
-    B200W_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM));
-    configured = true;
-  }
+  ensure_dynamic_smem(cross_attn_tc_kernel, XT_SMEM);
   CrossTcParams p;
   p.q = q; p.q_stride = q_stride; p.stream = stream; p.g_start = g_start; p.g_count = g_count;
   p.n_live_groups = n_live_groups; p.n_heads = n_heads; p.blocks_per_stream = n_layers * 2 * n_heads;
   p.layer_block0 = 2 * layer * n_heads; p.len = len; p.out = out; p.out_stride = out_stride;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.allow_split = allow_split;
-  // scratch: zero-initialised once by the owner; [num_sms counters][num_sms * pieces * record]
+  const int n_tiles = (len + 127) >> 7;
+  if (pieces < 1 || pieces > XT_MAX_PIECES || n_tiles % pieces != 0) pieces = 1;
+  p.pieces = pieces;
+  B200W_REQUIRE(n_groups * n_heads <= XT_MAX_ITEMS, "cross_attention_tc: too many (group, head) items");
+  // scratch: zero-initialised once by the owner; [XT_MAX_ITEMS counters][XT_MAX_ITEMS * pieces * record]
   p.counters = static_cast<int*>(scratch);
-  p.partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + ((XT_CTAS_PER_SM * num_sms() * sizeof(int) + 255) & ~(size_t)255));
+  p.partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + ((XT_MAX_ITEMS * sizeof(int) + 255) & ~(size_t)255));
   p.trace = g_xt_trace;
-  const int items = n_groups * n_heads;
+  const int units = n_groups * n_heads * pieces;
   const int max_ctas = XT_CTAS_PER_SM * num_sms();
-  launch_pdl(cross_attn_tc_kernel, dim3(items < max_ctas ? items : max_ctas), dim3(192), (size_t)XT_SMEM, cs, tm, p);
+  launch_pdl(cross_attn_tc_kernel, dim3(units < max_ctas ? units : max_ctas), dim3(192), (size_t)XT_SMEM, cs, tm, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }
@@ -1311,11 +1295,7 @@ template <int XQ>
 static void launch_cross_attn(const CrossAttnParams& p, int n_groups, int n_heads, cudaStream_t stream) {
   const int len_pad = (p.len + 31) & ~31;
   const size_t smem = sizeof(float) * (XQ * HD + 8 + (size_t)XQ * len_pad + (size_t)XW * XQ * HD);
-  static size_t configured = 0;
-  if (smem > configured) {
-    B200W_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_kernel<XQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  ensure_dynamic_smem(cross_attn_kernel<XQ>, smem);
   launch_pdl(cross_attn_kernel<XQ>, dim3(n_groups, n_heads), dim3(XW * 32), smem, stream, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());

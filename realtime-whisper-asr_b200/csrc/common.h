@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <stdexcept>
 #include <string>
 
@@ -55,7 +56,14 @@ struct Error : public std::runtime_error {
   }                                                  \
   return 0;
 
-int num_sms();
+int num_sms();  // SM count of the CURRENT device (cached per device)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (device, function): remember what each device was given
+// (grow-only) instead of a per-process flag, so engines on several GPUs of one process all get configured.
+void ensure_dynamic_smem(const void* func, size_t bytes);
+template <typename... KArgs>
+inline void ensure_dynamic_smem(void (*kernel)(KArgs...), size_t bytes) {
+  ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes);
+}
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -88,8 +96,8 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 }
 #endif
 
-// launch counter (bench.py reports gpu_launches from this)
-extern unsigned long long g_launch_count;
-#define B200W_COUNT_LAUNCH() (++::b200w::g_launch_count)
+// launch counter (bench.py reports gpu_launches from this); engines may run on several host threads
+extern std::atomic<unsigned long long> g_launch_count;
+#define B200W_COUNT_LAUNCH() (::b200w::g_launch_count.fetch_add(1, std::memory_order_relaxed))
 
 }  // namespace b200w

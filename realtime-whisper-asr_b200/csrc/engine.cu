@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -96,6 +97,52 @@ struct PinnedBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
+// Optional per-op timing of the decoder pass (B200W_DECODE_PROFILE=1; eager launches only): CUDA events
+// around every op, summed per op type and printed when the decode call returns.
+struct OpTimer {
+  bool on = false;
+  bool forced = false;  // b200w_op_profile_enable: decode steps run eagerly so that every op can be bracketed
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int id; cudaEvent_t a, b; double work; };
+  std::vector<Rec> recs;
+  double tot_ms[16] = {0}, tot_work[16] = {0};
+  long long tot_n[16] = {0};
+  double next_work = 0;  // algorithmic bytes / flops of the op about to be recorded (set by the caller)
+  const char* names[16] = {"embed", "layernorm", "qkv_gemm", "kv_scatter", "self_attn", "out_gemm", "cq_gemm",
+                           "cross_attn", "cout_gemm", "fc1_gemm", "fc2_gemm", "logits_gemm", "sample", "fork",
+                           "final_ln", "other"};
+  cudaEvent_t ev() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void collect(const char* tag) {
+    if (!on || recs.empty()) return;
+    double tot[16] = {0};
+    int cnt[16] = {0};
+    for (auto& r : recs) {
+      float ms = 0;
+      cudaEventSynchronize(r.b);
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      tot[r.id] += ms;
+      cnt[r.id]++;
+      tot_ms[r.id] += ms;
+      tot_work[r.id] += r.work;
+      tot_n[r.id]++;
+    }
+    if (getenv("B200W_DECODE_PROFILE")) {
+      fprintf(stderr, "[b200w op profile] %s\n", tag);
+      for (int i = 0; i < 16; ++i)
+        if (cnt[i]) fprintf(stderr, "   %-12s n=%6d total %9.3f ms  avg %8.2f us\n", names[i], cnt[i], tot[i], 1000.0 * tot[i] / cnt[i]);
+    }
+    recs.clear();
+    used = 0;
+  }
+};
 }  // namespace
 
 struct b200w_engine {
@@ -151,6 +198,11 @@ struct b200w_engine {
   // in-graph probe: events around the decode cross attention of one layer, every decode step (bench roofline)
   cudaEvent_t xev0 = nullptr, xev1 = nullptr;
   bool xev_recorded = false;
+  double probe_ms = 0, probe_bytes = 0;  // totals of that probe since the last reset
+  long long probe_n = 0;
+  OpTimer optimer;        // per-op event timing of eager decode passes (profiling aid)
+  std::mutex mu;          // one host thread at a time inside an engine call (workspaces are per engine)
+  SkinnyCache* skinny_cache = nullptr;  // launch records of this engine's decode-step GEMMs (freed with it)
 };
 
 namespace {
@@ -203,71 +255,23 @@ void linear(const bf16* A, int M, int K, const Lin& l, int N, void* out, int64_t
   gemm_bf16(g, s);
 }
 
-// Optional per-op timing of the decoder pass (B200W_DECODE_PROFILE=1; eager launches only): CUDA events
-// around every op, summed per op type and printed when the decode call returns.
-struct OpTimer {
-  bool on = false;
-  bool forced = false;  // b200w_op_profile_enable: decode steps run eagerly so that every op can be bracketed
-  std::vector<cudaEvent_t> pool;
-  size_t used = 0;
-  struct Rec { int id; cudaEvent_t a, b; double work; };
-  std::vector<Rec> recs;
-  double tot_ms[16] = {0}, tot_work[16] = {0};
-  long long tot_n[16] = {0};
-  double next_work = 0;  // algorithmic bytes / flops of the op about to be recorded (set by the caller)
-  const char* names[16] = {"embed", "layernorm", "qkv_gemm", "kv_scatter", "self_attn", "out_gemm", "cq_gemm",
-                           "cross_attn", "cout_gemm", "fc1_gemm", "fc2_gemm", "logits_gemm", "sample", "fork",
-                           "final_ln", "other"};
-  cudaEvent_t ev() {
-    if (used == pool.size()) {
-      cudaEvent_t e;
-      cudaEventCreate(&e);
-      pool.push_back(e);
-    }
-    return pool[used++];
-  }
-  void collect(const char* tag) {
-    if (!on || recs.empty()) return;
-    double tot[16] = {0};
-    int cnt[16] = {0};
-    for (auto& r : recs) {
-      float ms = 0;
-      cudaEventSynchronize(r.b);
-      cudaEventElapsedTime(&ms, r.a, r.b);
-      tot[r.id] += ms;
-      cnt[r.id]++;
-      tot_ms[r.id] += ms;
-      tot_work[r.id] += r.work;
-      tot_n[r.id]++;
-    }
-    if (getenv("B200W_DECODE_PROFILE")) {
-      fprintf(stderr, "[b200w op profile] %s\n", tag);
-      for (int i = 0; i < 16; ++i)
-        if (cnt[i]) fprintf(stderr, "   %-12s n=%6d total %9.3f ms  avg %8.2f us\n", names[i], cnt[i], tot[i], 1000.0 * tot[i] / cnt[i]);
-    }
-    recs.clear();
-    used = 0;
-  }
-};
-static OpTimer g_optimer;
 struct OpScope {
+  OpTimer& t;
   int id;
   cudaStream_t s;
   cudaEvent_t a = nullptr;
   double work = 0;
-  OpScope(int id_, cudaStream_t s_) : id(id_), s(s_) {
-    if (g_optimer.on) { a = g_optimer.ev(); work = g_optimer.next_work; g_optimer.next_work = 0; cudaEventRecord(a, s); }
+  OpScope(OpTimer& t_, int id_, cudaStream_t s_) : t(t_), id(id_), s(s_) {
+    if (t.on) { a = t.ev(); work = t.next_work; t.next_work = 0; cudaEventRecord(a, s); }
   }
   ~OpScope() {
-    if (a) { cudaEvent_t b = g_optimer.ev(); cudaEventRecord(b, s); g_optimer.recs.push_back({id, a, b, work}); }
+    if (a) { cudaEvent_t b = t.ev(); cudaEventRecord(b, s); t.recs.push_back({id, a, b, work}); }
   }
 };
-#define OP(id) OpScope _op_scope_##id(id, s)
+#define OP(id) OpScope _op_scope_##id(e->optimer, id, s)
 // Step probe: CUDA events around the tensor-core cross attention of ONE decoder layer in every decode step --
 // inside the captured step graph as external event-record nodes -- so that bench.py can time the dominant
 // kernel inside its timed region (a graph replay cannot be bracketed from outside).  Totals since the last reset.
-static double g_probe_ms = 0, g_probe_bytes = 0;
-static long long g_probe_n = 0;
 static void probe_record(cudaEvent_t ev, cudaStream_t s) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   B200W_CHECK_CUDA(cudaStreamIsCapturing(s, &st));
@@ -286,6 +290,14 @@ static unsigned ablate_mask() {
 // that enough CTAs stream the weights; the partial sums are handed to the next LayerNorm.
 // Decode steps (at most 256 rows): weight-row-major tcgen05 GEMM (skinny.cu), split along K into fp32 slabs
 // in e->d_split that the consumer reduces.  Returns the slab description.
+// Key-range pieces per (stream, head) item of the decode-step cross attention: a constant (never a function of
+// the batch), so results are batch-invariant.  Measured on the bench workload (640 items, 296 CTAs; ms per decode
+// step, profiles/r02_cross_pieces.txt): 1 piece 3.99, 2: 4.33, 3: 4.49, 4: 4.66, 6: 5.23 -- every extra unit costs a
+// softmax bubble in the load stream, which outweighs the better balance, so items are computed whole.
+static int cross_step_pieces() {
+  static const int n = getenv("B200W_XT_PIECES") ? atoi(getenv("B200W_XT_PIECES")) : 1;
+  return n;
+}
 static bool use_skinny() {
   static const bool on = getenv("B200W_NO_SKINNY") == nullptr;
   return on;
@@ -301,6 +313,7 @@ SplitReduce skinny_split(b200w_engine* e, const bf16* A, int M, int K, const Lin
     g.W = l.w; g.ldw = K; g.N = N; g.K = K;
     g.out = e->d_split.as<float>() + (long long)r0 * N; g.out_fp32 = 1; g.ldo = N;
     g.splits = splits; g.split_stride = (int64_t)M * N;
+    g.cache = e->skinny_cache;
     skinny_gemm(g, s);
   }
   SplitReduce r;
@@ -315,34 +328,10 @@ SplitReduce residual_linear(b200w_engine* e, const bf16* A, int M, int K, const 
   const int d = e->d;
   // measured (tools/gemm_skinny_bench.py): 7 splits for K = d, 10 for K = 4d; more only adds slab traffic
   if (use_skinny() && e->step_pass && d % 128 == 0) return skinny_split(e, A, M, K, l, d, K > 2 * d ? 10 : 7, s);
-  const int splits = gemm_suggest_splits(M, d, K);
-  if (splits <= 1 || (size_t)splits * M * d * 4 > e->d_split.bytes) {
-    linear(A, M, K, l, d, x, d, 1, 0, x, 1, d, s);
-    return SplitReduce{};
-  }
-  GemmDesc g;
-  g.A = A;
-  g.a_rows = M;
-  g.a_cols = K;
-  g.a_row_stride = K;
-  g.W = l.w;
-  g.N = d;
-  g.K = K;
-  g.w_row_stride = K;
-  g.out_rows = M;
-  g.out = e->d_split.p;
-  g.out_fp32 = 1;
-  g.out_row_stride = d;
-  g.split_k = splits;
-  g.split_stride = (int64_t)M * d;
-  g.force_bn = 64;
-  gemm_bf16(g, s);
-  SplitReduce r;
-  r.partial = e->d_split.as<float>();
-  r.n = splits;
-  r.stride = (long long)M * d;
-  r.bias = l.b;
-  return r;
+  // prompt / alignment / language passes: one unsplit GEMM with the residual in its epilogue.  (A split-K factor
+  // chosen from the row count would make a stream's rounding depend on how many streams share the pass.)
+  linear(A, M, K, l, d, x, d, 1, 0, x, 1, d, s);
+  return SplitReduce{};
 }
 
 // ----------------------------------------------------------------------------------- decoder pass
@@ -560,11 +549,12 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
       const bool tc = use_tc && m.max_group <= CROSS_GROUP;
       // decode steps are op 7, with their algorithmic bytes: K and V of every live (group, head), read once;
       // prompt / alignment passes are timed under "other"
-      if (step_tc) g_optimer.next_work = (double)m.n_live_host * e->H * 2.0 * e->Tenc * HEAD_DIM * 2.0;
-      OpScope _op_scope_x(step_tc ? 7 : 15, s);
+      if (step_tc) e->optimer.next_work = (double)m.n_live_host * e->H * 2.0 * e->Tenc * HEAD_DIM * 2.0;
+      OpScope _op_scope_x(e->optimer, step_tc ? 7 : 15, s);
       // many rows per stream (prompts, alignment): flash kernel, K/V streamed once per (stream, head)
+      // (every non-step pass, whatever its segment lengths: the kernel choice must not depend on the batch)
       static const bool use_flash = getenv("B200W_NO_CROSS_FLASH") == nullptr;
-      if (use_flash && !e->step_pass && m.max_seg > CROSS_GROUP) {
+      if (use_flash && !e->step_pass) {
         cross_attention_flash(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, n, m.stream, m.seg_start,
                               m.seg_count, m.n_segs, m.max_seg, attn, s);
         if (c.head_export) {
@@ -572,10 +562,10 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
           cross_attention(c, m.n_groups, e->H, m.max_group, s, nullptr);
         }
       } else if (tc) {
-        const bool probe = step_tc && e->step_pass && l == e->Ld / 2 && !g_optimer.on;
+        const bool probe = step_tc && e->step_pass && l == e->Ld / 2 && !e->optimer.on;
         if (probe) probe_record(e->xev0, s);
         cross_attention_tc(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, d, m.stream, m.g_start, m.g_count,
-                           m.n_live, m.n_groups, attn, d, 0.125f, e->x_tc.p, s, e->step_pass ? 1 : 0);
+                           m.n_live, m.n_groups, attn, d, 0.125f, e->x_tc.p, s, e->step_pass ? cross_step_pieces() : 1);
         if (probe) { probe_record(e->xev1, s); e->xev_recorded = true; }
         if (c.head_export) {
           c.export_only = 1;
@@ -622,6 +612,7 @@ void logits_for_rows(b200w_engine* e, const int* sel_rows_dev, int n_sel, cudaSt
         g.X = hsel + (long long)r0 * e->d; g.ldx = e->d; g.M = std::min(256, n_sel - r0);
         g.W = emb.w; g.ldw = e->d; g.N = e->V; g.K = e->d;
         g.out = e->logits.as<float>() + (long long)r0 * e->ldv; g.out_fp32 = 1; g.ldo = e->ldv;
+        g.cache = e->skinny_cache;
         skinny_gemm(g, s);
       }
     } else {
@@ -652,6 +643,7 @@ int b200w_engine_create(const b200w_model_config* cfg, b200w_engine** out) {
   B200W_REQUIRE(ndev > 0, "no CUDA device (there is no CPU fallback)");
   b200w_engine* e = new b200w_engine();
   e->cfg = *cfg;
+  e->skinny_cache = skinny_cache_create();
   e->d = cfg->d_model; e->H = cfg->n_heads; e->Le = cfg->n_enc_layers; e->Ld = cfg->n_dec_layers;
   e->V = cfg->n_vocab; e->ldv = (cfg->n_vocab + 7) / 8 * 8; e->Tctx = cfg->n_text_ctx; e->Tenc = cfg->n_audio_ctx;
   *out = e;
@@ -669,7 +661,9 @@ int b200w_engine_destroy(b200w_engine* e) {
     for (DevBuf* b : bufs) b->release();
     e->h_meta.release();
     e->h_out.release();
+    cudaDeviceSynchronize();  // nothing of this engine may still be in flight
     for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.exec);
+    skinny_cache_destroy(e->skinny_cache);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->join_event) cudaEventDestroy(e->join_event);
     if (e->xev0) cudaEventDestroy(e->xev0);
@@ -748,8 +742,8 @@ int b200w_engine_finalize(b200w_engine* e) {
     e->d_split.alloc(need);
   }
   e->x_split.alloc(cross_attention_scratch_bytes(64, e->H));
-  e->x_tc.alloc(cross_attention_tc_scratch_bytes() + 256);
-  B200W_CHECK_CUDA(cudaMemset(e->x_tc.p, 0, cross_attention_tc_scratch_bytes() + 256));  // splits only happen below ~148 tiles
+  e->x_tc.alloc(cross_attention_tc_scratch_bytes());
+  B200W_CHECK_CUDA(cudaMemset(e->x_tc.p, 0, cross_attention_tc_scratch_bytes()));  // arrival counters start at zero
   e->slots_per_stream = e->Tctx * e->cfg.max_beam;
   e->total_slots = (long long)e->slots_per_stream * Bm;
   e->kpool.alloc((size_t)e->Ld * e->total_slots * d * 2);
@@ -792,6 +786,7 @@ int b200w_engine_finalize(b200w_engine* e) {
 int b200w_encode(b200w_engine* e, const void* windows_dev, int B, void* enc_out_dev, void* stream) {
   B200W_API_BEGIN
   B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  std::lock_guard<std::mutex> engine_lock(e->mu);
   B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int d = e->d, T = e->Tenc, M = B * T;
@@ -820,6 +815,7 @@ int b200w_encode(b200w_engine* e, const void* windows_dev, int B, void* enc_out_
 int b200w_cross_kv(b200w_engine* e, const void* enc_out_dev, int B, void* cross_kv_dev, void* stream) {
   B200W_API_BEGIN
   B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  std::lock_guard<std::mutex> engine_lock(e->mu);
   B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
   const int N = e->Ld * 2 * e->d;
   GemmDesc g;
@@ -891,6 +887,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
                  float* no_speech_out_host, void* stream) {
   B200W_API_BEGIN
   B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  std::lock_guard<std::mutex> engine_lock(e->mu);
   B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
   B200W_REQUIRE(opts && opts->beam_size >= 1 && opts->beam_size <= e->cfg.max_beam, "beam size out of range");
   // everything below runs on the engine's own stream, ordered after the caller's stream
@@ -917,7 +914,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
 
   e->xev_recorded = false;
   const bool timing = getenv("B200W_DECODE_TIMING") != nullptr;
-  g_optimer.on = g_optimer.forced || (getenv("B200W_DECODE_PROFILE") != nullptr && !e->use_graphs);
+  e->optimer.on = e->optimer.forced || (getenv("B200W_DECODE_PROFILE") != nullptr && !e->use_graphs);
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration<double, std::milli>(now() - t0).count();
@@ -1086,7 +1083,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
       e->step_graphs.clear();
       e->h_meta.grew = e->h_out.grew = false;
     }
-    if (e->use_graphs && step >= 2 && !g_optimer.on) {
+    if (e->use_graphs && step >= 2 && !e->optimer.on) {
       for (auto& g : e->step_graphs)
         if (g.ckv == ckv && g.B == B && g.K == K && g.parity == cur && g.opts_hash == opts_hash) exec = g.exec;
       if (!exec) {
@@ -1109,11 +1106,11 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
         e->step_graphs.push_back({ckv, B, K, cur, opts_hash, exec});
       }
       B200W_CHECK_CUDA(cudaGraphLaunch(exec, s));
-      g_launch_count += e->launches_per_step;
+      g_launch_count.fetch_add(e->launches_per_step, std::memory_order_relaxed);
     } else {
-      const unsigned long long before = g_launch_count;
+      const unsigned long long before = g_launch_count.load();
       enqueue_step(pm, meta_bytes, cur);
-      e->launches_per_step = g_launch_count - before;
+      e->launches_per_step = g_launch_count.load() - before;
     }
     cur ^= 1;
     B200W_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -1121,9 +1118,9 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     if (e->xev_recorded) {  // the probe events were (re)recorded by this step: graph replay or eager launch
       float pms = 0.f;
       if (cudaEventElapsedTime(&pms, e->xev0, e->xev1) == cudaSuccess) {
-        g_probe_ms += pms;
-        g_probe_n += 1;
-        g_probe_bytes += (double)pm.n_live_host * e->H * 2.0 * e->Tenc * HEAD_DIM * 2.0;
+        e->probe_ms += pms;
+        e->probe_n += 1;
+        e->probe_bytes += (double)pm.n_live_host * e->H * 2.0 * e->Tenc * HEAD_DIM * 2.0;
       } else {
         cudaGetLastError();
       }
@@ -1182,7 +1179,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     }
     t_book += ms_since(t_s2);
   }
-  g_optimer.collect("decode (prefill + steps)");
+  e->optimer.collect("decode (prefill + steps)");
   if (timing)
     fprintf(stderr, "[b200w_decode] B=%d K=%d steps=%d prefill+first=%.2f ms, per step: fill %.3f ms, launch+gpu %.3f ms, "
             "bookkeeping %.3f ms, total %.1f ms\n", B, K, n_steps, t_prefill, t_fill / std::max(n_steps, 1),
@@ -1210,6 +1207,7 @@ int b200w_decoder_logits(b200w_engine* e, const void* cross_kv_dev, int B, const
                          const int32_t* token_lens_host, float* logits_out_dev, void* stream) {
   B200W_API_BEGIN
   B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  std::lock_guard<std::mutex> engine_lock(e->mu);
   B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   HostMeta hm;
@@ -1248,6 +1246,7 @@ int b200w_detect_language(b200w_engine* e, const void* cross_kv_dev, int B, int3
                           const int32_t* lang_ids_host, int32_t n_lang, float* probs_out_host, void* stream) {
   B200W_API_BEGIN
   B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  std::lock_guard<std::mutex> engine_lock(e->mu);
   B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch && n_lang >= 1 && n_lang <= 128, "arguments out of range");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   HostMeta hm;
@@ -1279,6 +1278,7 @@ int b200w_align(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t*
                 float* tok_prob_out_host, int32_t max_tok, void* stream) {
   B200W_API_BEGIN
   B200W_REQUIRE(e && e->finalized, "engine not finalized");
+  std::lock_guard<std::mutex> engine_lock(e->mu);
   B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch && n_align >= 1, "arguments out of range");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Tenc = e->Tenc;
@@ -1378,31 +1378,41 @@ int b200w_align(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t*
 
 }  // extern "C"
 
-extern "C" int b200w_op_profile_enable(int on) {
-  g_optimer.forced = on != 0;
+extern "C" int b200w_op_profile_enable(b200w_engine* e, int on) {
+  if (!e) return -1;
+  std::lock_guard<std::mutex> lock(e->mu);
+  OpTimer& t = e->optimer;
+  t.forced = on != 0;
   if (on) {
-    for (int i = 0; i < 16; ++i) { g_optimer.tot_ms[i] = 0; g_optimer.tot_work[i] = 0; g_optimer.tot_n[i] = 0; }
+    for (int i = 0; i < 16; ++i) { t.tot_ms[i] = 0; t.tot_work[i] = 0; t.tot_n[i] = 0; }
   }
   return 0;
 }
-extern "C" int b200w_op_profile_read(int op, const char** name, double* total_ms, int64_t* launches, double* work) {
-  if (op < 0 || op >= 16) return -1;
-  if (name) *name = g_optimer.names[op];
-  if (total_ms) *total_ms = g_optimer.tot_ms[op];
-  if (launches) *launches = g_optimer.tot_n[op];
-  if (work) *work = g_optimer.tot_work[op];
+extern "C" int b200w_op_profile_read(b200w_engine* e, int op, const char** name, double* total_ms, int64_t* launches,
+                                     double* work) {
+  if (!e || op < 0 || op >= 16) return -1;
+  std::lock_guard<std::mutex> lock(e->mu);
+  const OpTimer& t = e->optimer;
+  if (name) *name = t.names[op];
+  if (total_ms) *total_ms = t.tot_ms[op];
+  if (launches) *launches = t.tot_n[op];
+  if (work) *work = t.tot_work[op];
   return 0;
 }
 
-extern "C" int b200w_step_probe_reset(void) {
-  g_probe_ms = 0;
-  g_probe_bytes = 0;
-  g_probe_n = 0;
+extern "C" int b200w_step_probe_reset(b200w_engine* e) {
+  if (!e) return -1;
+  std::lock_guard<std::mutex> lock(e->mu);
+  e->probe_ms = 0;
+  e->probe_bytes = 0;
+  e->probe_n = 0;
   return 0;
 }
-extern "C" int b200w_step_probe_read(double* total_ms, int64_t* launches, double* bytes) {
-  if (total_ms) *total_ms = g_probe_ms;
-  if (launches) *launches = g_probe_n;
-  if (bytes) *bytes = g_probe_bytes;
+extern "C" int b200w_step_probe_read(b200w_engine* e, double* total_ms, int64_t* launches, double* bytes) {
+  if (!e) return -1;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (total_ms) *total_ms = e->probe_ms;
+  if (launches) *launches = e->probe_n;
+  if (bytes) *bytes = e->probe_bytes;
   return 0;
 }

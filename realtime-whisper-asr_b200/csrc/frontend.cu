@@ -681,13 +681,8 @@ void logmel_launch(const float* audio, const long long* offsets, const long long
                    int* stream_max, int max_frames, cudaStream_t stream) {
   if (n_streams <= 0) return;
   const MelTables* tab = device_tables(n_mels);
-  static bool configured = false;
   const size_t smem = logmel_smem_bytes();
-  if (!configured) {
-    B200W_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-    configured = true;
-  }
+  ensure_dynamic_smem(logmel_kernel, smem);
   init_stream_max_kernel<<<cdiv(n_streams, 256), 256, 0, stream>>>(stream_max, n_streams);
   B200W_COUNT_LAUNCH();
   MelArgs a{audio, offsets, out_offsets, tile_prefix, out, stream_max, n_streams};
@@ -722,12 +717,7 @@ void dedup_features_launch(const float* audio, const long long* offsets, int n_c
   // many complex points (8 bytes each); 216 KB is what one CTA can take on sm_100a.
   B200W_REQUIRE(max_points <= 27648, "chunk too long for the shared-memory DFT (N <= 55296 even, 27648 odd)");
   size_t smem = (size_t)(max_points < 128 ? 128 : max_points) * 8;
-  static size_t configured = 0;
-  if (smem > configured) {
-    B200W_CHECK_CUDA(cudaFuncSetAttribute(dedup_features_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  ensure_dynamic_smem(dedup_features_kernel, smem);
   DedupArgs a{audio, offsets, out, raw_out, sample_rate};
   dedup_features_kernel<<<n_chunks, 512, smem, stream>>>(a, (int)(smem / 8));
   B200W_COUNT_LAUNCH();

@@ -477,12 +477,7 @@ template <int BN, int STAGES, int MP>
 static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p,
                         cudaStream_t stream) {
   constexpr int smem_bytes = STAGES * (MP * A_BYTES + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200W_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, MP>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = true;
-  }
+  ensure_dynamic_smem(gemm_tcgen05_kernel<BN, STAGES, MP>, smem_bytes);
   p.n_tiles = cdiv(p.N, BN);
   p.m_tiles_per_batch = cdiv(p.out_rows, BM * MP);
   p.total_tiles = p.n_tiles * p.m_tiles_per_batch * p.batches;
@@ -577,17 +572,6 @@ void gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   else if (bn == 64 && pair) launch_gemm<64, 5, 2>(tmA, tmB, p, stream);
   else if (bn == 64) launch_gemm<64, 8, 1>(tmA, tmB, p, stream);
   else throw Error("force_bn must be 64, 128 or 256");
-}
-
-int gemm_suggest_splits(int M, int N, int K) {
-  // skinny GEMMs (decode steps): enough CTAs to stream the weights at full HBM bandwidth
-  // the split count depends on (N, K) only, so a row's result does not change with the number of
-  // rows batched next to it (as long as the call stays below the one-wave threshold)
-  if (cdiv(M, BM) * cdiv(N, 64) >= num_sms()) return 1;
-  const int want = num_sms() / cdiv(N, 64);  // keep all work items in a single wave
-  const int kb = K / BK;
-  int sp = want < kb / 4 ? want : kb / 4;
-  return sp < 1 ? 1 : (sp > 16 ? 16 : sp);
 }
 
 void conv1d_k3(const bf16* x, const bf16* w, const float* bias, const float* addend, void* out, int B,

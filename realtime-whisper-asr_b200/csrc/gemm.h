@@ -44,8 +44,6 @@ struct GemmDesc {
 };
 
 void gemm_bf16(const GemmDesc& d, cudaStream_t stream);
-// number of K splits that gives a skinny [M x N x K] GEMM enough CTAs (1 = do not split)
-int gemm_suggest_splits(int M, int N, int K);
 
 // conv1d, kernel 3, padding 1, stride 1|2 over time-major x bf16 [B][T][C]; w bf16 [N][3C] tap-major;
 // out = GELU(conv + bias) + addend (fp32 [T_out][N], shared by all batches; may be null).

@@ -47,7 +47,8 @@ __device__ __forceinline__ long long sk_gtime() { long long t; asm volatile("mov
 // block with a single coalesced load and lets the TMA unit read the descriptors from the same
 // record (measured 1.9 us faster per launch than a 350-byte kernel-parameter block, which lives in
 // the constant bank and is cold in every freshly launched CTA).  Records are created once per
-// distinct call (a decode step repeats the same calls on the same buffers) and never freed.
+// distinct call (a decode step repeats the same calls on the same buffers) and live in a SkinnyCache
+// that its owner (an engine) frees.
 struct __align__(128) SkinnyLaunch {
   CUtensorMap tmW, tmX;
   SkinnyParams p;
@@ -225,6 +226,37 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_gemm_kernel(const Skinny
   if (p.trace && threadIdx.x == 0) { SK_TRACE(8); p.trace[blockIdx.x * 16 + 9] = sk_gtime(); }
 }
 
+struct SkinnyKey {
+  const void *x, *w, *bias, *out;
+  long long ldx, ldw, ldo, ss;
+  int M, N, K, act, of, sp, tr;
+  const void* trace;
+  bool operator<(const SkinnyKey& o) const {
+    return std::tie(x, w, bias, out, ldx, ldw, ldo, ss, M, N, K, act, of, sp, tr, trace) <
+           std::tie(o.x, o.w, o.bias, o.out, o.ldx, o.ldw, o.ldo, o.ss, o.M, o.N, o.K, o.act, o.of, o.sp, o.tr, o.trace);
+  }
+};
+struct SkinnyCache {
+  std::mutex mu;  // engines may be driven from several host threads
+  std::map<SkinnyKey, SkinnyLaunch*> recs;
+  int device = -1;
+};
+SkinnyCache* skinny_cache_create() { return new SkinnyCache(); }
+void skinny_cache_destroy(SkinnyCache* c) {
+  if (!c) return;
+  for (auto& kv : c->recs) cudaFree(kv.second);
+  delete c;
+}
+static SkinnyCache* default_cache() {
+  static SkinnyCache* per_dev[64] = {nullptr};
+  static std::mutex mu;
+  int dev = 0;
+  B200W_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (!per_dev[dev & 63]) per_dev[dev & 63] = new SkinnyCache();
+  return per_dev[dev & 63];
+}
+
 static long long* g_sk_trace = nullptr;
 void skinny_set_trace(void* buf) { g_sk_trace = static_cast<long long*>(buf); }
 
@@ -268,48 +300,42 @@ void skinny_gemm(const SkinnyDesc& d, cudaStream_t stream) {
   make_tmap_bf16_3d(&tmW, d.W, d.K, d.N, 1, d.ldw, (uint64_t)d.N * d.ldw, SK_BK, p.tile_rows);
   make_tmap_bf16_3d(&tmX, d.X, d.K, d.M, 1, d.ldx, (uint64_t)d.M * d.ldx, SK_BK, p.Mpad);
   // launch record: one per distinct (operands, shape, epilogue), reused by every later identical call
-  struct Key {
-    const void *x, *w, *bias, *out;
-    long long ldx, ldw, ldo, ss;
-    int M, N, K, act, of, sp, tr;
-    const void* trace;
-    bool operator<(const Key& o) const {
-      return std::tie(x, w, bias, out, ldx, ldw, ldo, ss, M, N, K, act, of, sp, tr, trace) <
-             std::tie(o.x, o.w, o.bias, o.out, o.ldx, o.ldw, o.ldo, o.ss, o.M, o.N, o.K, o.act, o.of, o.sp, o.tr, o.trace);
+  const SkinnyKey key{d.X, d.W, d.bias, d.out, d.ldx, d.ldw, d.ldo, d.split_stride, d.M, d.N, d.K, d.act, d.out_fp32, splits, p.tile_rows, g_sk_trace};
+  SkinnyCache* cache = d.cache ? d.cache : default_cache();
+  std::lock_guard<std::mutex> lock(cache->mu);
+  int dev = 0;
+  B200W_CHECK_CUDA(cudaGetDevice(&dev));
+  if (cache->device < 0) cache->device = dev;
+  B200W_REQUIRE(cache->device == dev, "skinny_gemm: launch-record cache used from two devices");
+  auto it = cache->recs.find(key);
+  if (it == cache->recs.end()) {
+    if (!d.cache && cache->recs.size() >= 512) {  // the shared default is bounded: drop everything once idle
+      B200W_CHECK_CUDA(cudaDeviceSynchronize());
+      for (auto& kv : cache->recs) cudaFree(kv.second);
+      cache->recs.clear();
     }
-  };
-  static std::map<Key, SkinnyLaunch*> cache;
-  static std::mutex cache_mutex;  // engines may be driven from several host threads
-  std::lock_guard<std::mutex> lock(cache_mutex);
-  const Key key{d.X, d.W, d.bias, d.out, d.ldx, d.ldw, d.ldo, d.split_stride, d.M, d.N, d.K, d.act, d.out_fp32, splits, p.tile_rows, g_sk_trace};
-  auto it = cache.find(key);
-  if (it == cache.end()) {
     SkinnyLaunch host;
     host.tmW = tmW;
     host.tmX = tmX;
     host.p = p;
-    SkinnyLaunch* dev = nullptr;
-    B200W_CHECK_CUDA(cudaMalloc(&dev, sizeof(SkinnyLaunch)));
-    B200W_CHECK_CUDA(cudaMemcpy(dev, &host, sizeof(host), cudaMemcpyHostToDevice));
-    it = cache.emplace(key, dev).first;
+    SkinnyLaunch* devrec = nullptr;
+    B200W_CHECK_CUDA(cudaMalloc(&devrec, sizeof(SkinnyLaunch)));
+    B200W_CHECK_CUDA(cudaMemcpy(devrec, &host, sizeof(host), cudaMemcpyHostToDevice));
+    it = cache->recs.emplace(key, devrec).first;
   }
   const SkinnyLaunch* rec = it->second;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  auto launch = [&](auto kernel, size_t& configured) {
-    if (smem > configured) {
-      B200W_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+  auto launch = [&](auto kernel) {
+    ensure_dynamic_smem(kernel, smem);
     launch_pdl(kernel, dim3(p.n_tiles * splits), dim3(SK_THREADS), smem, stream, rec);
   };
-  static size_t cfg[3] = {0, 0, 0};
   if (d.out_fp32) {
     B200W_REQUIRE(d.act == 0, "GELU is only built for bf16 outputs");
-    launch(skinny_gemm_kernel<0, 1>, cfg[0]);
+    launch(skinny_gemm_kernel<0, 1>);
   } else if (d.act == 1) {
-    launch(skinny_gemm_kernel<1, 0>, cfg[1]);
+    launch(skinny_gemm_kernel<1, 0>);
   } else {
-    launch(skinny_gemm_kernel<0, 0>, cfg[2]);
+    launch(skinny_gemm_kernel<0, 0>);
   }
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());

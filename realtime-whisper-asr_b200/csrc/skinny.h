@@ -4,6 +4,12 @@
 
 namespace b200w {
 
+// Launch records (TMA descriptors + parameters, in device memory) of the distinct calls made through one owner.
+// An engine owns one and frees it when it is destroyed; calls without an owner share a bounded process-wide one.
+struct SkinnyCache;
+SkinnyCache* skinny_cache_create();
+void skinny_cache_destroy(SkinnyCache* c);  // caller guarantees no launch that uses the records is in flight
+
 struct SkinnyDesc {
   const bf16* X = nullptr;  // activations [M][K], row stride ldx (elements)
   int64_t ldx = 0;
@@ -19,6 +25,7 @@ struct SkinnyDesc {
   int splits = 1;
   int tile_rows = 128;  // weight rows per CTA: 128 or 64 (64 needs M >= 64)
   int64_t split_stride = 0;  // elements between slabs
+  SkinnyCache* cache = nullptr;  // owner of the launch record (null: the shared default)
 };
 void skinny_gemm(const SkinnyDesc& d, cudaStream_t stream);
 void skinny_set_trace(void* dev_buf);  // development aid: per-CTA timestamps of later launches

@@ -134,14 +134,17 @@ def test_skinny_gemm(lib, cuda_device, M, N, K, splits):
     assert (out16[:, :N].float() - refg).abs().max().item() <= 2e-2 * max(1.0, refg.abs().max().item())
 
 
-@pytest.mark.parametrize("n_streams,H,L,layer,length,counts", [
-    (2, 6, 2, 1, 1500, [5, 5]),                 # two streams, beam 5: 12 items, all split into key-range pieces
-    (32, 20, 1, 0, 1500, [5] * 32),             # the bench shape: 640 items = whole rounds + split tail round
-    (3, 4, 1, 0, 1500, [1, 8, 0]),              # greedy row, full group of 8, finished stream (skipped)
-    (2, 8, 1, 0, 700, [3, 2]),                  # ragged key count (6 tiles, last one partly out of range)
-    (40, 8, 1, 0, 1500, [5] * 40),              # 320 items > 296 CTAs with remainder
+@pytest.mark.parametrize("n_streams,H,L,layer,length,counts,pieces", [
+    (2, 6, 2, 1, 1500, [5, 5], 3),              # two streams, beam 5: 12 items x 3 key-range pieces
+    (32, 20, 1, 0, 1500, [5] * 32, 3),          # the bench shape: 640 items x 3 pieces over 296 CTAs
+    (32, 20, 1, 0, 1500, [5] * 32, 1),          # the same, whole items (prompt-sized passes)
+    (3, 4, 1, 0, 1500, [1, 8, 0], 4),           # greedy row, full group of 8, finished stream (skipped)
+    (2, 8, 1, 0, 700, [3, 2], 2),               # ragged key count (6 tiles, last one partly out of range)
+    (2, 8, 1, 0, 700, [3, 2], 6),               # one tile per piece; the last piece is mostly out of range
+    (40, 8, 1, 0, 1500, [5] * 40, 2),           # 640 units > 296 CTAs with remainder
+    (5, 6, 1, 0, 1500, [5] * 5, 5),             # 5 does not divide 12 tiles: falls back to whole items
 ])
-def test_cross_attention_tc(lib, cuda_device, n_streams, H, L, layer, length, counts):
+def test_cross_attention_tc(lib, cuda_device, n_streams, H, L, layer, length, counts, pieces):
     """Decode-step cross attention (tcgen05) vs fp32 softmax(q k^T / 8) v on the same bf16 inputs."""
     g = torch.Generator(device="cpu").manual_seed(n_streams * 131 + H + length)
     d = H * 64
@@ -162,7 +165,7 @@ def test_cross_attention_tc(lib, cuda_device, n_streams, H, L, layer, length, co
         _lib.check(lib.b200w_cross_attention_tc(kv.data_ptr(), n_streams, L, layer, H, length, q.data_ptr(),
                                                 stream.data_ptr(), g_start.data_ptr(), g_count.data_ptr(),
                                                 n_live.data_ptr(), len(counts), out.data_ptr(), 0.125,
-                                                scratch.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                                scratch.data_ptr(), pieces, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     worst = 0.0
     for s_i, c in enumerate(counts):
@@ -179,6 +182,17 @@ def test_cross_attention_tc(lib, cuda_device, n_streams, H, L, layer, length, co
         assert (out[r0 + c:r0 + rows_per].float() == 7.0).all(), "dead rows of a live group must not be written"
     # P is rounded to bf16 before P.V and the output is bf16: |v| <~ 4, so 2^-8 relative of a few units
     assert worst <= 3e-2, f"max abs err {worst}"
+    # batch invariance, bit for bit: the first live stream ALONE in a launch gives exactly its rows of the batch
+    s0 = live[0]
+    out1 = torch.full((n_rows, d), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    one = torch.tensor([1], dtype=torch.int32, device=cuda_device)
+    _lib.check(lib.b200w_cross_attention_tc(kv.data_ptr(), n_streams, L, layer, H, length, q.data_ptr(),
+                                            stream.data_ptr(), g_start.data_ptr(), g_count.data_ptr(),
+                                            one.data_ptr(), len(counts), out1.data_ptr(), 0.125,
+                                            scratch.data_ptr(), pieces, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    r0, c = s0 * rows_per, counts[s0]
+    assert torch.equal(out1[r0:r0 + c], out[r0:r0 + c]), "a stream's rows depend on what else is in the launch"
 
 
 @pytest.mark.parametrize("n_streams,H,L,layer,length,counts", [
