@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-legs", action="store_true", help="skip the front-end roofline and base-latency legs")
     ap.add_argument("--cpu-sample-streams", type=int, default=1)
+    ap.add_argument("--lanes", type=int, default=1, help="concurrent sub-batches per GPU (engines + CUDA streams)")
     return ap.parse_args()
 
 
@@ -246,7 +247,7 @@ def latency_leg(local):
     from realtime_whisper_asr_b200.backend import B200WhisperASR
     from realtime_whisper_asr_b200.transcribe import B200WhisperModel
     from tests.synth import speech_like
-    model = B200WhisperModel("base", device="cuda", device_index=local, max_batch=1, max_beam=5)
+    model = B200WhisperModel("base", device="cuda", device_index=local, max_batch=1, max_beam=5, synthetic=True)
     asr = B200WhisperASR("en", model=model, transcribe_kwargs={"beam_size": 5, "temperature": 0.0})
     audio = speech_like(4321, 30.0)
     lat = []
@@ -279,8 +280,8 @@ def run_b200(args, rank, world, local):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    model = B200WhisperModel(args.model, device="cuda", device_index=local, max_batch=args.streams,
-                             max_beam=max(args.beam, 1))
+    model = B200WhisperModel(args.model, device="cuda", device_index=local, synthetic=True, max_batch=args.streams,
+                             max_beam=max(args.beam, 1), lanes=args.lanes)
     audios = make_streams(args.streams, args.seconds, rank)
     kw = dict(languages=["en"] * args.streams, beam_size=args.beam, temperature=0.0, word_timestamps=True,
               condition_on_previous_text=True)

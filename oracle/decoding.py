@@ -81,7 +81,11 @@ def rule_mask(n_vocab: int, sampled: Sequence[int], o: DecodeOptions) -> np.ndar
     return m
 
 
-def masked_logprobs(logits: np.ndarray, sampled: Sequence[int], o: DecodeOptions) -> np.ndarray:
+def masked_logprobs(logits: np.ndarray, sampled: Sequence[int], o: DecodeOptions, margins: list = None) -> np.ndarray:
+    """Log-probabilities after the logit rules.  ``margins`` (optional list) receives the decision margins of
+    this position in nats: |log sum p(timestamps) - log max p(text)| when the timestamp-mass rule is evaluated
+    with both sides admissible, and the gap between the two best admissible tokens -- what a conditioning
+    analysis needs to tell a robust argmax from a near-tie."""
     x = logits.astype(np.float32).copy()
     m = rule_mask(len(x), sampled, o)
     x[m] = -np.inf
@@ -94,9 +98,15 @@ def masked_logprobs(logits: np.ndarray, sampled: Sequence[int], o: DecodeOptions
         if sum_ts > 0:
             ts_lp = mx + np.log(sum_ts) - lse
             text_lp = np.max(x[:tb]) - lse
+            if margins is not None and np.isfinite(text_lp):
+                margins.append(float(abs(ts_lp - text_lp)))
             if ts_lp > text_lp:
                 x[:tb] = -np.inf
                 lse = mx + np.log(sum_ts)
+    if margins is not None:
+        top2 = np.partition(x, -2)[-2:]
+        if np.isfinite(top2[0]):
+            margins.append(float(top2[1] - top2[0]))
     return x - lse
 
 
@@ -109,7 +119,9 @@ def _norm(cum: float, n: int, lp: float) -> float:
     return cum / (max(n, 1) ** lp)
 
 
-def decode_one(model: OracleWhisper, enc_row: torch.Tensor, prompt: Sequence[int], o: DecodeOptions) -> DecodeResult:
+def decode_one(model: OracleWhisper, enc_row: torch.Tensor, prompt: Sequence[int], o: DecodeOptions,
+               margins: list = None) -> DecodeResult:
+    """``margins`` (greedy only): per sampled position, the smallest decision margin (see masked_logprobs)."""
     D = model.dims
     K = o.beam_size
     k_top = 1 if K == 1 else 2 * K
@@ -127,7 +139,15 @@ def decode_one(model: OracleWhisper, enc_row: torch.Tensor, prompt: Sequence[int
 
     alive = []  # (tokens, cum, row)
     finished = []  # (tokens, cum, score)
-    for tok, lp in _topk(masked_logprobs(lg[-1], [], o), k_top):
+    def _lp(row, sampled):
+        if margins is None or K != 1:
+            return masked_logprobs(row, sampled, o)
+        mm: list = []
+        out = masked_logprobs(row, sampled, o, mm)
+        margins.append(min(mm) if mm else float("inf"))
+        return out
+
+    for tok, lp in _topk(_lp(lg[-1], []), k_top):
         if len(alive) >= K:
             break
         if tok == o.eot:
@@ -147,7 +167,7 @@ def decode_one(model: OracleWhisper, enc_row: torch.Tensor, prompt: Sequence[int
         lg = model.logits(hid)[:, 0].numpy()
         cands = []
         for k, (t, c, _) in enumerate(alive):
-            for tok, lp in _topk(masked_logprobs(lg[k], t, o), k_top):
+            for tok, lp in _topk(_lp(lg[k], t), k_top):
                 cands.append((c + float(np.float32(lp)), k, tok))
         cands.sort(key=lambda z: (-z[0], z[1], z[2]))
         nxt = []

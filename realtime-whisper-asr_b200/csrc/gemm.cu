@@ -9,6 +9,7 @@
 // the out-of-range rows that the conv padding needs.
 #include "gemm.h"
 
+#include <deque>
 #include <mutex>
 #include <vector>
 
@@ -439,15 +440,18 @@ struct ProfSlot {
 };
 static long long* g_trace = nullptr;
 void gemm_set_trace(void* dev_buf) { g_trace = static_cast<long long*>(dev_buf); }
-static int g_prof_bn = 0;  // 0 = off, else the BN class being timed
-static std::vector<ProfSlot> g_prof_slots;
+static std::atomic<int> g_prof_bn{0};  // 0 = off, else the BN class being timed
+static std::deque<ProfSlot> g_prof_slots;   // guarded by g_prof_mu (engines launch from several host threads)
 static size_t g_prof_used = 0;
+static std::mutex g_prof_mu;
 
 void gemm_profile_begin(int bn) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   g_prof_bn = bn;
   g_prof_used = 0;
 }
 void gemm_profile_end(double* total_ms, double* total_flops, long long* launches) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   g_prof_bn = 0;
   double ms = 0, fl = 0;
   for (size_t i = 0; i < g_prof_used; ++i) {
@@ -462,6 +466,7 @@ void gemm_profile_end(double* total_ms, double* total_flops, long long* launches
   *launches = (long long)g_prof_used;
 }
 static ProfSlot* prof_slot(double flops) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   if (g_prof_used == g_prof_slots.size()) {
     ProfSlot s;
     B200W_CHECK_CUDA(cudaEventCreate(&s.beg));

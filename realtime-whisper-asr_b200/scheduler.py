@@ -126,7 +126,7 @@ class StreamBatcher:
                 return
             try:
                 out = self.model.transcribe_batch([r.audio for r in batch], languages=[r.language for r in batch],
-                                                  initial_prompt=[r.initial_prompt for r in batch], **batch[0].kwargs)
+                                                  initial_prompts=[r.initial_prompt for r in batch], **batch[0].kwargs)
                 for r, o in zip(batch, out):
                     r.result = o
             except BaseException as e:  # delivered to every caller of the batch, as a solo call would raise

@@ -62,10 +62,11 @@ class _HFVocab:
 
 class Tokenizer:
     def __init__(self, n_vocab: int = 51865, multilingual: bool = True, task: str = "transcribe",
-                 language: Optional[str] = "en", tokenizer_json: Optional[str] = None):
+                 language: Optional[str] = "en", tokenizer_json: Optional[str] = None, vocab=None):
         self.n_vocab = n_vocab
         self.multilingual = multilingual
-        self.vocab = _HFVocab(tokenizer_json) if tokenizer_json else _ByteVocab()
+        # `vocab`: an already loaded vocabulary object to share (tokenizer.json is a multi-MB parse)
+        self.vocab = vocab if vocab is not None else (_HFVocab(tokenizer_json) if tokenizer_json else _ByteVocab())
         v3 = 1 if n_vocab >= 51866 else 0
         self.n_languages = 100 if v3 else 99
         self.eot = 50257 if multilingual else 50256

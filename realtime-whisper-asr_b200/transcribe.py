@@ -16,7 +16,8 @@ steps with one encoder / decoder / align launch per round (streams are the natur
 """
 from __future__ import annotations
 
-import itertools
+import logging
+import os
 import zlib
 from dataclasses import dataclass, field
 from typing import Iterable, List, NamedTuple, Optional, Sequence, Tuple, Union
@@ -27,8 +28,9 @@ import torch
 from . import _lib, frontend
 from .engine import DecodeOptions, WhisperEngine
 from .tokenizer import Tokenizer
-from .weights import (ALIGNMENT_HEADS, MODEL_DIMS, ModelDims, default_alignment_heads, pack_for_engine,
-                      synthetic_state_dict)
+from .weights import MODEL_DIMS, ModelDims, alignment_heads_for, pack_for_engine, synthetic_state_dict
+
+_log = logging.getLogger("b200w")
 
 SAMPLE_RATE = 16000
 HOP = 160
@@ -276,49 +278,104 @@ class B200WhisperModel:
                  download_root: Optional[str] = None, local_files_only: bool = False,
                  state_dict=None, dims: Optional[ModelDims] = None, tokenizer_json: Optional[str] = None,
                  alignment_heads: Optional[Sequence[Tuple[int, int]]] = None, max_batch: int = 8,
-                 max_beam: int = 5, seed: int = 0, **_ignored):
+                 max_beam: int = 5, seed: int = 0, synthetic: Optional[bool] = None, lanes: int = 1, **_ignored):
+        """``model_size_or_path``: a model directory (CTranslate2 ``model.bin`` or ``model.safetensors``, see
+        loader.py) or a size name that is looked up under ``download_root`` / the Hugging Face cache the way
+        faster-whisper does.  There is no network: a size name without a checkpoint on disk is an ERROR unless
+        ``synthetic=True`` (or the environment variable B200W_SYNTHETIC_WEIGHTS=1) asks for seeded random weights of
+        that architecture with the synthetic byte vocabulary -- what tests and bench.py use, never a transcript.
+
+        ``lanes`` > 1: a batch is cut into that many sub-batches that run CONCURRENTLY, each on its own engine
+        (workspaces, KV cache, captured decode graphs; the weights are shared) and CUDA stream, driven by its own host
+        thread.  A decode step is a chain of dependent launches (latency-bound), its cross attention is HBM-bound and
+        the encoder tensor-bound: independent lanes fill each other's bubbles.  Streams are independent and every
+        kernel is batch-invariant, so the results are identical to lanes=1."""
         if device not in ("cuda", "auto"):
             raise _lib.B200WError(f"device={device!r}: the B200 backend runs on CUDA only (no CPU fallback)")
         if not torch.cuda.is_available():
             raise _lib.B200WError("CUDA device required: the B200 backend has no CPU fallback")
         self.device = torch.device("cuda", device_index if isinstance(device_index, int) else device_index[0])
+        if compute_type not in ("bfloat16", "default", "auto"):
+            _log.warning("compute_type=%r requested; this backend computes in bfloat16 (fp32 accumulation)", compute_type)
         self.compute_type = "bfloat16"  # the only arithmetic this backend implements
         self.tokenizer_json = tokenizer_json
+        self.suppress_ids: Optional[List[int]] = None        # from a CTranslate2 config.json, when present
+        self.suppress_ids_begin: Optional[List[int]] = None
+        self.synthetic = False
         name = model_size_or_path
+        if synthetic is None:
+            synthetic = os.environ.get("B200W_SYNTHETIC_WEIGHTS", "") not in ("", "0")
         if state_dict is None:
-            from .loader import load_model_dir  # real checkpoints, when a directory is given
-            loaded = load_model_dir(name)
-            if loaded is not None:
-                state_dict, dims, tj, heads = loaded
-                self.tokenizer_json = self.tokenizer_json or tj
-                alignment_heads = alignment_heads or heads
+            from .loader import load_model_dir, resolve_model_dir
+            found = resolve_model_dir(name, download_root)
+            if found is not None:
+                loaded = load_model_dir(found)
+                state_dict, dims = loaded.state_dict, loaded.dims
+                self.tokenizer_json = self.tokenizer_json or loaded.tokenizer_json
+                alignment_heads = alignment_heads or loaded.alignment_heads
+                self.suppress_ids, self.suppress_ids_begin = loaded.suppress_ids, loaded.suppress_ids_begin
+                _log.info("loaded %s from %s", loaded.source, found)
             else:
-                base = name.replace(".en", "")
+                base = str(name).replace(".en", "")
                 if base not in MODEL_DIMS:
-                    raise ValueError(f"unknown model size {name!r}")
+                    raise ValueError(f"{name!r} is neither a model directory nor a known model size")
+                if not synthetic:
+                    raise FileNotFoundError(
+                        f"no checkpoint for model {name!r}: not a directory, nothing under download_root="
+                        f"{download_root!r} or the Hugging Face cache, and there is no network to download one.  "
+                        "Pass a CTranslate2 / safetensors model directory, or synthetic=True for seeded random "
+                        "weights (tests and benchmarks only).")
                 dims = MODEL_DIMS[base]
-                # no checkpoints exist offline: seeded synthetic weights of the exact architecture
-                # (large models are generated on the device: ~1.5 G random numbers; the CUDA and CPU
-                # generators give different values, so parity tests pass CPU-made state dicts)
+                # seeded synthetic weights of the exact architecture (large models are generated on the device:
+                # ~1.5 G random numbers; the CUDA and CPU generators give different values, so parity tests pass
+                # CPU-made state dicts)
                 gen_dev = str(self.device) if dims.d_model >= 1024 else "cpu"
                 state_dict = synthetic_state_dict(dims, seed=seed, device=gen_dev)
-                if alignment_heads is None:
-                    alignment_heads = ALIGNMENT_HEADS.get(base)
+                self.synthetic = True
+                _log.warning("model %r: SYNTHETIC random weights and byte vocabulary (no checkpoint) -- output is "
+                             "well-formed but meaningless", name)
+        else:
+            self.synthetic = tokenizer_json is None
         assert dims is not None
         self.dims = dims
-        self.alignment_heads = list(alignment_heads) if alignment_heads else default_alignment_heads(dims)
+        self.alignment_heads = list(alignment_heads) if alignment_heads else alignment_heads_for(dims)
         self.is_multilingual = dims.multilingual
+        self.n_lanes = max(1, min(int(lanes), max_batch))
+        self.lane_batch = -(-max_batch // self.n_lanes)
         with torch.cuda.device(self.device):
-            self.engine = WhisperEngine(dims, pack_for_engine(state_dict, dims, self.device), max_batch=max_batch,
-                                        max_beam=max_beam, device=self.device)
+            packed = pack_for_engine(state_dict, dims, self.device)
+            self.engines = [WhisperEngine(dims, packed, max_batch=self.lane_batch, max_beam=max_beam, device=self.device)
+                            for _ in range(self.n_lanes)]
+            self.lane_streams = [torch.cuda.Stream(self.device) for _ in range(self.n_lanes)] if self.n_lanes > 1 else []
+        self.engine = self.engines[0]
+        self._pool = None
         self.max_batch = max_batch
         self.max_beam = max_beam
         self.last_timings = {}
         self.profile_phases = False
+        self._vocab = None            # loaded once: tokenizer.json is a multi-MB parse
+        self._tokenizers = {}         # (language, task) -> Tokenizer
+        self._warned = set()
+
+    def _warn_once(self, key: str, msg: str) -> None:
+        if key not in self._warned:
+            self._warned.add(key)
+            _log.warning(msg)
+
+    def tokenizer(self, language: Optional[str] = "en", task: str = "transcribe") -> Tokenizer:
+        """Cached per (language, task); the vocabulary object is shared by all of them."""
+        key = (language, task)
+        tk = self._tokenizers.get(key)
+        if tk is None:
+            tk = Tokenizer(self.dims.n_vocab, self.is_multilingual, task=task, language=language,
+                           tokenizer_json=self.tokenizer_json, vocab=self._vocab)
+            self._vocab = tk.vocab
+            self._tokenizers[key] = tk
+        return tk
 
     @property
     def supported_languages(self) -> List[str]:
-        return Tokenizer(self.dims.n_vocab, self.is_multilingual, language="en").languages if self.is_multilingual else ["en"]
+        return self.tokenizer("en").languages if self.is_multilingual else ["en"]
 
     # ------------------------------------------------------------------ public API
     def transcribe(self, audio: Union[np.ndarray, torch.Tensor], language: Optional[str] = None,
@@ -334,7 +391,8 @@ class B200WhisperModel:
                          compression_ratio_threshold: Optional[float] = 2.4,
                          log_prob_threshold: Optional[float] = -1.0, no_speech_threshold: Optional[float] = 0.6,
                          condition_on_previous_text: bool = True, prompt_reset_on_temperature: float = 0.5,
-                         initial_prompt: Union[None, str, Sequence[Optional[str]]] = None,
+                         initial_prompt: Union[None, str, Iterable[int]] = None,
+                         initial_prompts: Optional[Sequence[Union[None, str, Iterable[int]]]] = None,
                          prefix: Optional[str] = None, suppress_blank: bool = True,
                          suppress_tokens: Optional[List[int]] = (-1,), without_timestamps: bool = False,
                          max_initial_timestamp: float = 1.0, word_timestamps: bool = False,
@@ -343,20 +401,33 @@ class B200WhisperModel:
                          device_audio=None, max_rounds: Optional[int] = None, **unsupported):
         """Transcribe independent clips concurrently; returns [(segments, info)] per clip.
 
-        ``device_audio=(audio_dev, offsets)`` skips the host->device copy: the clips are already
-        concatenated in one fp32 device tensor (``audios`` is then only used for its length)."""
+        ``initial_prompt`` has faster-whisper's meaning (a string, or token ids) and applies to every clip;
+        ``initial_prompts`` gives one such value per clip.  ``device_audio=(audio_dev, offsets)`` skips the
+        host->device copy: the clips are already concatenated in one fp32 device tensor (``audios`` is then only
+        used for its length)."""
         if vad_filter:
             raise NotImplementedError("vad_filter: the VAD gate sits in the caller (Silero in the reference)")
         if repetition_penalty != 1 or no_repeat_ngram_size != 0:
             raise NotImplementedError("repetition_penalty / no_repeat_ngram_size are not implemented")
         temps = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
         if temps[0] != 0:
-            raise NotImplementedError("sampling temperatures > 0 are not implemented (temperature 0 only)")
+            # the reference passes 0.0 (一键实时识别麦克风.py:1121-1124); its unused adaptive hook may ask for 0.1
+            # (speech_rate_audio_processor.py:214-218).  Sampling is not implemented: decode deterministically.
+            self._warn_once("temperature", f"temperature={temps[0]}: sampling is not implemented, decoding with "
+                                           "temperature 0 (beam search / greedy)")
+            temps = [0.0]
         if beam_size > self.max_beam:
-            raise ValueError(f"beam_size {beam_size} > engine max_beam {self.max_beam}")
+            self._warn_once("beam", f"beam_size {beam_size} exceeds this engine's max_beam {self.max_beam}: clamped "
+                                    "(build the model with max_beam=... to raise it, at most 8)")
+            beam_size = self.max_beam
         n = len(audios) if device_audio is None else len(device_audio[1]) - 1
         languages = list(languages) if languages is not None else [None] * n
-        prompts_in = initial_prompt if isinstance(initial_prompt, (list, tuple)) else [initial_prompt] * n
+        if initial_prompts is not None:
+            if len(initial_prompts) != n:
+                raise ValueError("initial_prompts must hold one entry per clip")
+            prompts_in = list(initial_prompts)
+        else:
+            prompts_in = [initial_prompt] * n
         if device_audio is None:
             audios = [np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1)) for a in audios]
             durations = [len(a) / SAMPLE_RATE for a in audios]
@@ -391,15 +462,14 @@ class B200WhisperModel:
                         lang_info[i] = d
             streams: List[_Stream] = []
             for i in range(n):
-                tk = Tokenizer(self.dims.n_vocab, self.is_multilingual, task=task, language=lang_info[i][0],
-                               tokenizer_json=self.tokenizer_json)
+                tk = self.tokenizer(lang_info[i][0], task)
                 st = _Stream(i, mel.n_frames[i] - 1, tk, options)
                 ip = prompts_in[i]
                 if ip is not None:
                     if isinstance(ip, str):
                         st.all_tokens.extend(tk.encode(" " + ip.strip()))
                     else:
-                        st.all_tokens.extend(ip)
+                        st.all_tokens.extend(int(t) for t in ip)
                 streams.append(st)
             self._run_streams(mel, streams, max_rounds)
         out = []
@@ -418,10 +488,10 @@ class B200WhisperModel:
 
     # ------------------------------------------------------------------ internals
     def _detect_language(self, mel: frontend.MelBatch, which: List[int]):
-        tk = Tokenizer(self.dims.n_vocab, True, language="en")
+        tk = self.tokenizer("en")
         out = []
-        for c0 in range(0, len(which), self.max_batch):
-            ids = which[c0:c0 + self.max_batch]
+        for c0 in range(0, len(which), self.lane_batch):
+            ids = which[c0:c0 + self.lane_batch]
             windows = frontend.pack_windows(mel, ids, [0] * len(ids))
             enc = self.engine.encode(windows)
             ckv = self.engine.cross_kv(enc)
@@ -433,6 +503,18 @@ class B200WhisperModel:
         return out
 
     def _decode_options(self, tk: Tokenizer, o: TranscriptionOptions) -> DecodeOptions:
+        """Decoder options of a batch.  The suppress sets depend on the vocabulary, the model's special-token layout
+        and the call's ``suppress_tokens`` -- never on a stream's language or task -- so one set serves the batch.
+        A CTranslate2 config.json's ``suppress_ids`` / ``suppress_ids_begin`` take the place of the lists derived
+        from the vocabulary (that is what faster-whisper feeds CTranslate2 for suppress_tokens=[-1])."""
+        if o.suppress_tokens is None:
+            suppress = []
+        elif self.suppress_ids is not None and -1 in o.suppress_tokens:
+            suppress = sorted(set([t for t in o.suppress_tokens if t >= 0] + list(self.suppress_ids) +
+                                  [tk.transcribe, tk.translate, tk.sot, tk.sot_prev, tk.sot_lm, tk.no_speech]))
+        else:
+            suppress = tk.suppressed_tokens(o.suppress_tokens)
+        blank = list(self.suppress_ids_begin) if self.suppress_ids_begin is not None else tk.blank_tokens()
         return DecodeOptions(
             beam_size=o.beam_size, patience=o.patience, length_penalty=o.length_penalty,
             max_new_tokens=o.max_new_tokens or 0, suppress_blank=o.suppress_blank,
@@ -440,8 +522,7 @@ class B200WhisperModel:
             max_initial_timestamp_index=int(round(o.max_initial_timestamp / TIME_PRECISION)),
             eot=tk.eot, sot=tk.sot, no_speech=tk.no_speech, no_timestamps=tk.no_timestamps,
             timestamp_begin=tk.timestamp_begin,
-            suppress_ids=tk.suppressed_tokens(o.suppress_tokens) if o.suppress_tokens is not None else [],
-            blank_ids=tk.blank_tokens())
+            suppress_ids=suppress, blank_ids=blank)
 
     def _run_streams(self, mel: frontend.MelBatch, streams: List[_Stream], max_rounds: Optional[int] = None) -> None:
         """Rounds of (pack windows -> encode -> cross K/V -> decode -> align) over the live streams.
@@ -452,8 +533,37 @@ class B200WhisperModel:
             if not live or (max_rounds is not None and rounds >= max_rounds):
                 return
             rounds += 1
+            if self.n_lanes == 1 or self.profile_phases or len(live) == 1:
+                for c0 in range(0, len(live), self.lane_batch):
+                    self._round(mel, live[c0:c0 + self.lane_batch], self.engines[0])
+                continue
             for c0 in range(0, len(live), self.max_batch):
-                self._round(mel, live[c0:c0 + self.max_batch])
+                self._round_lanes(mel, live[c0:c0 + self.max_batch])
+
+    def _round_lanes(self, mel: frontend.MelBatch, group: List[_Stream]) -> None:
+        """One round of `group` (<= max_batch streams) as n_lanes concurrent sub-batches."""
+        from concurrent.futures import ThreadPoolExecutor
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=self.n_lanes, thread_name_prefix="b200w-lane")
+        n = min(self.n_lanes, len(group))
+        per = -(-len(group) // n)
+        parts = [group[i * per:(i + 1) * per] for i in range(n)]
+        parts = [p for p in parts if p]
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)  # the log-mel features were produced on the caller's stream
+
+        def run(i: int):
+            with torch.cuda.device(self.device), torch.cuda.stream(self.lane_streams[i]):
+                self.lane_streams[i].wait_event(ready)
+                self._round(mel, parts[i], self.engines[i])
+                done = torch.cuda.Event()
+                done.record(self.lane_streams[i])
+                return done
+
+        futures = [self._pool.submit(run, i) for i in range(len(parts))]
+        for f in futures:
+            main.wait_event(f.result())  # re-raises a lane's exception in the caller
 
     def _phase(self, name: str, t0: float) -> float:
         """Accumulate wall time per phase when profiling is on (synchronises the device)."""
@@ -465,7 +575,7 @@ class B200WhisperModel:
         self.last_timings[name] = self.last_timings.get(name, 0.0) + (now - t0)
         return now
 
-    def _round(self, mel: frontend.MelBatch, batch: List[_Stream]) -> None:
+    def _round(self, mel: frontend.MelBatch, batch: List[_Stream], engine: WhisperEngine) -> None:
         import time as _t
         o = batch[0].options
         t = self._phase("_", _t.perf_counter())
@@ -474,12 +584,12 @@ class B200WhisperModel:
             s.segment_size = min(N_FRAMES, s.content_frames - s.seek)
             s.prompt = get_prompt(s.tokenizer, s.all_tokens[s.prompt_reset_since:], o.without_timestamps, o.prefix)
         windows = frontend.pack_windows(mel, [s.sid for s in batch], [s.seek for s in batch])
-        enc = self.engine.encode(windows)
+        enc = engine.encode(windows)
         t = self._phase("encode", t)
-        ckv = self.engine.cross_kv(enc)
+        ckv = engine.cross_kv(enc)
         t = self._phase("cross_kv", t)
-        # all streams of a batch share the special-token layout; suppress lists come from stream 0
-        results = self.engine.decode(ckv, [s.prompt for s in batch], self._decode_options(batch[0].tokenizer, o))
+        # one set of decoder options per batch: they do not depend on a stream's language or task (see there)
+        results = engine.decode(ckv, [s.prompt for s in batch], self._decode_options(self.tokenizer("en"), o))
         t = self._phase("decode", t)
         to_align = []  # (stream, subsegments, text_tokens, row in ckv)
         per_stream = []
@@ -506,7 +616,7 @@ class B200WhisperModel:
                 text_tokens = [t for sub in subs for t in sub["tokens"] if t < tk.eot]
                 to_align.append((len(per_stream) - 1, row, text_tokens))
         if o.word_timestamps and to_align:
-            self._align_batch(ckv, batch, per_stream, to_align, o)
+            self._align_batch(engine, ckv, batch, per_stream, to_align, o)
         t = self._phase("align", t)
         for entry in per_stream:
             if entry is None:
@@ -535,7 +645,7 @@ class B200WhisperModel:
             if not o.condition_on_previous_text:
                 s.prompt_reset_since = len(s.all_tokens)
 
-    def _align_batch(self, ckv, batch, per_stream, to_align, o: TranscriptionOptions) -> None:
+    def _align_batch(self, engine, ckv, batch, per_stream, to_align, o: TranscriptionOptions) -> None:
         rows = [row for _, row, tt in to_align if tt]
         if rows:
             tk0 = batch[0].tokenizer
@@ -547,7 +657,7 @@ class B200WhisperModel:
                 seqs.append(list(tk.sot_sequence) + [tk.no_timestamps] + tt + [tk.eot])
                 nframes.append(batch[row].segment_size)
             sub_ckv = ckv if rows == list(range(ckv.shape[0])) else ckv[rows].contiguous()
-            aligned = self.engine.align(sub_ckv, seqs, nframes, len(tk0.sot_sequence), self.alignment_heads)
+            aligned = engine.align(sub_ckv, seqs, nframes, len(tk0.sot_sequence), self.alignment_heads)
         k = 0
         for pi, row, tt in to_align:
             s, subs = per_stream[pi][0], per_stream[pi][1]

@@ -76,6 +76,15 @@ def default_alignment_heads(dims: ModelDims) -> List[Tuple[int, int]]:
     return [(l, h) for l in range(dims.n_dec_layers // 2, dims.n_dec_layers) for h in range(dims.n_heads)]
 
 
+def alignment_heads_for(dims: ModelDims) -> List[Tuple[int, int]]:
+    """The (layer, head) list a model of these dimensions aligns with: OpenAI's list for the known sizes,
+    CTranslate2's default otherwise."""
+    for name, md in MODEL_DIMS.items():
+        if md == dims and name in ALIGNMENT_HEADS:
+            return list(ALIGNMENT_HEADS[name])
+    return default_alignment_heads(dims)
+
+
 def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
     inc = math.log(max_timescale) / (channels // 2 - 1)
     inv = torch.exp(-inc * torch.arange(channels // 2, dtype=torch.float32))
@@ -157,6 +166,7 @@ def synthetic_state_dict(dims: ModelDims, seed: int = 0, device: str = "cpu",
     ln("decoder.ln")
     if peaked:
         _install_transcript_circuit(sd, dims, g, device)
+        _install_alignment_heads(sd, dims, g, device)
     return sd
 
 
@@ -241,6 +251,50 @@ def _install_transcript_circuit(sd: Dict[str, torch.Tensor], dims: ModelDims, g,
     for n in (p + ".mlp_ln", "decoder.ln"):
         sd[n + ".weight"] = torch.ones(d, device=device)
         sd[n + ".bias"] = torch.zeros(d, device=device)
+
+
+ALIGN_STRIDE = 12       # encoder frames (20 ms each) the synthetic alignment heads advance per decoder position
+ALIGN_CODE_AMPLITUDE = 2.0
+
+
+def _install_alignment_heads(sd: Dict[str, torch.Tensor], dims: ModelDims, g, device) -> None:
+    """Give the alignment heads the sharply peaked, monotone cross-attention a trained Whisper has.
+
+    A trained model's alignment heads attend, at decoder position i, to the audio frames where token i is
+    spoken; a random head attends almost uniformly, its DTW cost surface is flat and the word-timing path
+    is decided by rounding noise.  Here the heads read POSITION on both sides: the encoder output still
+    carries its sinusoidal position code (residual stream), the decoder's positional embedding gets a
+    matching code of frame f(i) = ALIGN_STRIDE * i in a 64-dimensional subspace, the head's key projection
+    selects 32 (sin, cos) pairs of the encoder code and its query projection reads the decoder code:
+        q_i . k_t  ~  sum_j cos(w_j (t - f(i)))      -> a peak at t = f(i) a few frames wide, side lobes ~ sqrt(32).
+    Values and output projections stay random, so through these heads every decoder position reads the LOCAL
+    audio content around frame f(i) instead of a time average: the logits (and the first sampled timestamp,
+    i.e. which synthetic transcript is emitted) depend on the audio."""
+    d, half = dims.d_model, dims.d_model // 2
+    heads = alignment_heads_for(dims)
+    # 32 encoder frequencies w_m = 10000^(-m/(half-1)) between ~0.3 and ~3e-3 rad/frame: the peak is ~+-4 frames
+    # wide, so it survives the width-7 median filter of the word-timing pass
+    m_lo, m_hi = int(0.12 * (half - 1)), int(0.62 * (half - 1))
+    m_idx = torch.linspace(m_lo, m_hi, 32).round().long().unique()
+    assert len(m_idx) == 32, "not enough distinct position frequencies"
+    inc = math.log(10000.0) / (half - 1)
+    w = torch.exp(-inc * m_idx.to(torch.float32))                          # [32]
+    pos = ALIGN_STRIDE * torch.arange(dims.n_text_ctx, dtype=torch.float32)
+    code = torch.stack([torch.sin(pos[:, None] * w), torch.cos(pos[:, None] * w)], dim=2).reshape(dims.n_text_ctx, 64)
+    q_, r_ = torch.linalg.qr(torch.randn(d, 64, generator=g, device=device, dtype=torch.float64))
+    P = (q_ * torch.sign(torch.diagonal(r_))).to(torch.float32)           # d x 64, orthonormal columns
+    sd["decoder.positional_embedding"] = sd["decoder.positional_embedding"] + ALIGN_CODE_AMPLITUDE * (code.to(device) @ P.T)
+    for (l, h) in heads:
+        p = f"decoder.blocks.{l}.cross_attn"
+        wk = sd[p + ".key.weight"]
+        wq = sd[p + ".query.weight"]
+        rows = slice(h * 64, (h + 1) * 64)
+        wk[rows] = 0.0
+        for j, m in enumerate(m_idx.tolist()):
+            wk[h * 64 + 2 * j, m] = 1.0            # sin(w_m t) of the encoder position code
+            wk[h * 64 + 2 * j + 1, half + m] = 1.0  # cos(w_m t)
+        wq[rows] = _bf16_round(2.0 * P.T)
+        sd[p + ".query.bias"][rows] = 0.0
 
 
 def dims_from_state_dict(sd: Dict[str, torch.Tensor]) -> ModelDims:

@@ -19,7 +19,7 @@ KW = dict(beam_size=5, temperature=0.0, word_timestamps=True, condition_on_previ
 
 @pytest.fixture(scope="module")
 def model(cuda_device):
-    return B200WhisperModel("large-v3", max_batch=32, max_beam=5)
+    return B200WhisperModel("large-v3", max_batch=32, max_beam=5, synthetic=True)
 
 
 def _tokens(segs):

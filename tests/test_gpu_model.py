@@ -97,32 +97,44 @@ def test_decoder_logits_parity(which, request):
         assert e32 <= tol, e32
 
 
-def _decode_both(fx, beam, max_new, prev=()):
+def _decode_both(fx, beam, max_new, prev=(), margins=None):
     B = fx.enc.shape[0]
     kw = decode_option_kwargs(fx.md.n_vocab, beam_size=beam, max_new_tokens=max_new)
     # different language tokens / previous text steer the model into different transcripts
     prompts = [fx.prompt(tuple(x + 13 * b for x in prev), lang=7 * b) for b in range(B)]
     got = fx.engine.decode(fx.ckv, prompts, DecodeOptions(**kw))
-    ref = OD.decode(fx.o16, fx.enc16, prompts, OD.DecodeOptions(**kw))
+    ref = []
+    for b in range(B):
+        m = [] if (margins is not None and beam == 1) else None
+        ref.append(OD.decode_one(fx.o16, fx.enc16[b], prompts[b], OD.DecodeOptions(**kw), m))
+        if margins is not None:
+            margins.append(min(m) if m else None)
     return got, ref
 
 
 @pytest.mark.parametrize("which,beam", [("micro", 1), ("micro", 5), ("tiny", 1), ("tiny", 5)])
 def test_decode_tokens_match_oracle(which, beam, request):
+    """Engine decode vs oracle decode on the same encoder input.  Greedy: identical on every chunk whose smallest
+    decision margin (oracle/decoding.py) is above the bf16 noise (0.15 nats); a chunk below it is a coin flip for
+    any bf16 engine and is only listed.  Beam 5 (reported, not the north-star bar): rankings of near-tied hypotheses
+    may legitimately flip, so at most one chunk may differ.  The large sweep is tests/test_gpu_parity_sweep.py."""
     fx = request.getfixturevalue(which)
-    got, ref = _decode_both(fx, beam, 0, prev=(311, 422, 533, 644) if beam == 1 else ())
-    same = 0
+    margins = []
+    got, ref = _decode_both(fx, beam, 0, prev=(311, 422, 533, 644) if beam == 1 else (), margins=margins)
+    same, bad = 0, 0
     for b, (g, r) in enumerate(zip(got, ref)):
         ok = g.tokens == r.tokens
         same += ok
+        cond = beam != 1 or margins[b] is None or margins[b] >= 0.15
         if not ok:
             n = next((i for i, (x, y) in enumerate(zip(g.tokens, r.tokens)) if x != y), min(len(g.tokens), len(r.tokens)))
-            print(f"{which} beam{beam} chunk {b}: diverges at token {n}: {g.tokens[n:n+3]} vs {r.tokens[n:n+3]}")
+            print(f"{which} beam{beam} chunk {b} (margin {margins[b]}): diverges at token {n}: {g.tokens[n:n+3]} vs {r.tokens[n:n+3]}")
+            bad += cond
         assert abs(g.no_speech_prob - r.no_speech_prob) <= 1e-3 + 0.05 * r.no_speech_prob
         if ok:
-            assert abs(g.sum_logprob - r.sum_logprob) <= 0.05 * max(1.0, abs(r.sum_logprob))
-    print(f"{which} beam{beam}: {same}/{len(got)} chunks token-identical, lengths {[len(g.tokens) for g in got]}")
-    assert same == len(got), f"{same}/{len(got)} chunks token-identical"
+            assert abs(g.sum_logprob - r.sum_logprob) <= 0.15 + 0.05 * abs(r.sum_logprob)
+    print(f"{which} beam{beam}: {same}/{len(got)} chunks token-identical, lengths {[len(g.tokens) for g in got]}, margins {margins}")
+    assert bad <= (0 if beam == 1 else 1), f"{bad} well-conditioned chunks differ from the oracle"
 
 
 def test_timestamp_rules_hold(tiny_flat):
@@ -140,11 +152,13 @@ def test_timestamp_rules_hold(tiny_flat):
 
 
 def test_align_matches_oracle(tiny):
+    """Word-timing pass on the synthetic model's peaked alignment heads (weights._install_alignment_heads): the DTW
+    path -- index work -- must EQUAL the oracle's, the token probabilities agree to bf16 tolerance."""
     fx = tiny
     sp = fx.sp
-    rng = np.random.default_rng(9)
     sot_seq = [sp["sot"], sp["lang0"], sp["transcribe"]]
-    texts = [rng.integers(0, 50000, size=n).tolist() for n in (12, 3, 25)]
+    scripts = W.synthetic_transcripts(fx.md.n_vocab)
+    texts = [[t for t in scripts[j][:n] if t < sp["eot"]] for j, n in ((2, 40), (28, 9), (45, 70))]
     seqs = [sot_seq + [sp["no_timestamps"]] + t + [sp["eot"]] for t in texts]
     num_frames = [3000, 400, 1150]
     heads = W.ALIGNMENT_HEADS["tiny"]
@@ -153,17 +167,14 @@ def test_align_matches_oracle(tiny):
         ti, fi, tp = OA.align(fx.o16, fx.enc16[b], sot_seq, sp["no_timestamps"], sp["eot"], texts[b],
                               num_frames[b], heads)
         gti, gfi, gtp = got[b]
-        # a monotone path from (0,0) to (N-1,M-1): every step advances text, time or both
-        assert gti[0] == 0 and gfi[0] == 0 and gti[-1] == ti[-1] and gfi[-1] == fi[-1]
-        assert np.all(np.diff(gti) >= 0) and np.all(np.diff(gfi) >= 0)
-        assert np.all((np.diff(gti) + np.diff(gfi)) >= 1) and np.all(np.diff(gti) <= 1) and np.all(np.diff(gfi) <= 1)
         print(f"align seq{b}: path len {len(gti)} vs {len(ti)}, |prob err| {np.abs(gtp - tp).max():.3g}")
         assert np.allclose(gtp, tp, rtol=0.1, atol=1e-6)
-        # jump times (word boundaries): DTW paths may part ways where the cost surface is flat,
-        # so ask for 90 % of the boundaries within 2 frames (40 ms)
-        jumps_g = gfi[np.pad(np.diff(gti), (1, 0), constant_values=1).astype(bool)]
-        jumps_r = fi[np.pad(np.diff(ti), (1, 0), constant_values=1).astype(bool)]
-        assert np.mean(np.abs(jumps_g - jumps_r) <= 2) >= 0.9
+        assert np.array_equal(gti, ti) and np.array_equal(gfi, fi), f"seq {b}: DTW path differs from the oracle's"
+        # and the path follows the heads' ridge: one token every weights.ALIGN_STRIDE frames (+- the peak width)
+        jumps = gfi[np.pad(np.diff(gti), (1, 0), constant_values=1).astype(bool)]
+        inside = [j for i, j in enumerate(jumps) if 2 <= i and W.ALIGN_STRIDE * (i + 5) < num_frames[b] // 2]
+        steps = np.diff(inside)
+        assert len(steps) == 0 or abs(np.median(steps) - W.ALIGN_STRIDE) <= 2
 
 
 def test_detect_language(tiny):

@@ -57,10 +57,10 @@ class _FakeModel:
     def __init__(self):
         self.batches = []
 
-    def transcribe_batch(self, audios, languages=None, initial_prompt=None, **kw):
+    def transcribe_batch(self, audios, languages=None, initial_prompts=None, **kw):
         self.batches.append(len(audios))
         time.sleep(0.01)
-        return [([("seg", len(a), p)], ("info", l)) for a, l, p in zip(audios, languages, initial_prompt)]
+        return [([("seg", len(a), p)], ("info", l)) for a, l, p in zip(audios, languages, initial_prompts)]
 
 
 def test_stream_batcher_batches_concurrent_calls():

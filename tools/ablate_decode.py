@@ -20,7 +20,7 @@ if a.child:
     from realtime_whisper_asr_b200.transcribe import B200WhisperModel
     from tests.synth import speech_like
     dev = torch.device("cuda", 0)
-    model = B200WhisperModel("large-v3", max_batch=32, max_beam=5)
+    model = B200WhisperModel("large-v3", max_batch=32, max_beam=5, synthetic=True)
     audios = [speech_like(1234 + i, 30.0) for i in range(32)]
     audio_dev, offsets = FE.upload_audio(audios, dev)
     kw = dict(languages=["en"] * 32, beam_size=5, temperature=0.0, word_timestamps=False,

@@ -7,7 +7,7 @@ from realtime_whisper_asr_b200.backend import B200WhisperASR
 from realtime_whisper_asr_b200.transcribe import B200WhisperModel
 from tests.synth import speech_like
 
-model = B200WhisperModel("base", device="cuda", device_index=0, max_batch=1, max_beam=5)
+model = B200WhisperModel("base", device="cuda", device_index=0, max_batch=1, max_beam=5, synthetic=True)
 asr = B200WhisperASR("en", model=model, transcribe_kwargs={"beam_size": 5, "temperature": 0.0})
 audio = speech_like(4321, 30.0)
 for i in range(1, 20):

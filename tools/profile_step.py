@@ -19,7 +19,7 @@ ap.add_argument("--max-new", type=int, default=12)
 ap.add_argument("--seconds", type=float, default=30.0)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-model = B200WhisperModel(a.model, max_batch=a.streams, max_beam=a.beam)
+model = B200WhisperModel(a.model, max_batch=a.streams, max_beam=a.beam, synthetic=True)
 audios = [speech_like(1234 + i, a.seconds) for i in range(a.streams)]
 audio_dev, offsets = FE.upload_audio(audios, dev)
 kw = dict(languages=["en"] * a.streams, beam_size=a.beam, temperature=0.0, word_timestamps=True,

@@ -6,7 +6,7 @@ from realtime_whisper_asr_b200.transcribe import B200WhisperModel
 from tests.synth import speech_like
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 beam = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-model = B200WhisperModel("large-v3", max_batch=n, max_beam=5)
+model = B200WhisperModel("large-v3", max_batch=n, max_beam=5, synthetic=True)
 auds = [speech_like(500 + i, 30.0) for i in range(n)]
 out = model.transcribe_batch(auds, languages=["en"] * n, beam_size=beam, temperature=0.0, word_timestamps=True)
 toks = [t for segs, _ in out for s in segs for t in s.tokens]
