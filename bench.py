@@ -60,7 +60,16 @@ def parse_args():
     ap.add_argument("--no-side-legs", action="store_true", help="skip the front-end roofline and base-latency legs")
     ap.add_argument("--cpu-sample-streams", type=int, default=1)
     ap.add_argument("--lanes", type=int, default=1, help="concurrent sub-batches per GPU (engines + CUDA streams)")
-    return ap.parse_args()
+    ap.add_argument("--config", default="large32", choices=["large32", "small64"],
+                    help="large32: BASELINE configs[3] per-GPU share (default, one-shot 30 s chunks); small64: configs[2], "
+                         "whisper small, 64 streams per GPU, 60 s of audio per stream in 1 s increments through the "
+                         "batched streaming policy")
+    ap.add_argument("--stream-seconds", type=float, default=None, help="audio per stream in the streaming legs")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="time budget of the reference arm")
+    a = ap.parse_args()
+    if a.config == "small64":
+        a.model, a.streams = "small", 64
+    return a
 
 
 def dist_env():
@@ -124,9 +133,11 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------ CPU path
-def cpu_oracle_pass(model_name, audios, beam, threads=None):
+def cpu_oracle_pass(model_name, audios, beam, threads=None, precision="fp32"):
     """One pass of the hot path on the host cores with the oracle; returns seconds elapsed.
-    (bench.py's cpu_baseline / reference arm: the only place the oracle is executed here.)"""
+    (bench.py's cpu_baseline / reference arm: the only place the oracle is executed here.)
+    precision: "fp32", or "int8" = Linear layers as dynamically quantised s8 GEMMs (what the reference's CPU path
+    does through CTranslate2 compute_type="int8", /root/reference/一键实时识别麦克风.py:1147-1164)."""
     import torch
     from oracle import align as OA
     from oracle import decoding as OD
@@ -139,17 +150,18 @@ def cpu_oracle_pass(model_name, audios, beam, threads=None):
         torch.set_num_threads(threads)
     md = W.MODEL_DIMS[model_name]
     cache = cpu_oracle_pass.__dict__.setdefault("cache", {})
-    if model_name not in cache:
-        sd = W.synthetic_state_dict(md, seed=0)
+    if (model_name, "sd") not in cache:
+        cache[(model_name, "sd")] = W.synthetic_state_dict(md, seed=0)
+    if (model_name, precision) not in cache:
         dims = Dims(md.n_mels, md.d_model, md.n_heads, md.n_enc_layers, md.n_vocab, md.d_model, md.n_heads,
                     md.n_dec_layers)
-        cache[model_name] = OracleWhisper(sd, dims, "fp32")
-    model = cache[model_name]
+        cache[(model_name, precision)] = OracleWhisper(cache[(model_name, "sd")], dims, precision)
+    model = cache[(model_name, precision)]
     tk = Tokenizer(md.n_vocab, True, language="en")
     opts = OD.DecodeOptions(beam_size=beam, eot=tk.eot, sot=tk.sot, no_speech=tk.no_speech,
                             no_timestamps=tk.no_timestamps, timestamp_begin=tk.timestamp_begin,
                             suppress_ids=tk.suppressed_tokens([-1]), blank_ids=tk.blank_tokens())
-    heads = W.ALIGNMENT_HEADS.get(model_name) or W.default_alignment_heads(md)
+    heads = W.alignment_heads_for(md)
     t0 = time.perf_counter()
     with torch.no_grad():
         for a in audios:
@@ -164,6 +176,45 @@ def cpu_oracle_pass(model_name, audios, beam, threads=None):
     return time.perf_counter() - t0
 
 
+def cpu_config1(threads, precision, calls=4):
+    """BASELINE configs[0] shape on the host: whisper tiny, ONE stream fed in 1 s increments with the buffer trimmed at
+    15 s (what OnlineASRProcessor submits), greedy.  `calls` consecutive calls from the steady state (15 s buffers) are
+    timed; returns audio-s/s counting every re-submitted second, as the product's own RTFx does."""
+    from tests.synth import speech_like
+    audio = speech_like(4321, 30.0)
+    bufs = [audio[(i - 15) * SR: i * SR] for i in range(30 - calls + 1, 31)]
+    cpu_oracle_pass("tiny", bufs[:1], 1, threads=threads, precision=precision)  # warm-up: weights, packing
+    t = cpu_oracle_pass("tiny", bufs, 1, threads=threads, precision=precision)
+    return sum(len(b) for b in bufs) / SR / t
+
+
+def cpu_baseline_report(args, audios):
+    """cpu_baseline object: the configured workload on all cores in fp32 and int8 (the faster one is `value`), plus
+    the configs[0] shape at the reference-faithful 4 threads (CTranslate2's default intra-op count: the reference
+    passes its thread count as num_workers, /root/reference/asr_components.py:259-261) and at all cores."""
+    cores = os.cpu_count() or 1
+    sample = audios[: args.cpu_sample_streams]
+    out, best = {}, None
+    for prec in ("fp32", "int8"):
+        t = cpu_oracle_pass(args.model, sample, args.beam, threads=cores, precision=prec)
+        v = len(sample) * args.seconds / t
+        out[f"{prec}_{cores}t"] = {"audio_s_per_s": v, "seconds_of_cpu_work": t}
+        if best is None or v > best[0]:
+            best = (v, prec, t)
+    cfg1 = {}
+    for prec in ("fp32", "int8"):
+        for th in sorted({4, cores}):
+            cfg1[f"{prec}_{th}t"] = cpu_config1(th, prec)
+    return {"value": best[0], "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "sample": f"{len(sample)} of {args.streams} streams, one {args.seconds:g} s chunk, full path (log-mel, "
+                      f"encoder, beam-{args.beam} decode, word timing), PyTorch oracle on the host, {best[1]} Linear "
+                      f"layers ({best[2]:.1f} s of CPU work)",
+            "variants": out,
+            "config1_tiny_streaming_audio_s_per_s": cfg1,
+            "note": "oracle port, not faster-whisper/CTranslate2 (not installable offline); int8 = torch dynamic "
+                    "quantisation (s8 GEMMs on the x86 engine), the stand-in BASELINE.md section 4 names"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -171,19 +222,29 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     audios = make_streams(args.cpu_sample_streams, args.seconds, 0)
+    # which arithmetic is faster on this host (fp32 or int8 Linear layers)?  Probe on whisper tiny, then use it.
+    probe = {p: cpu_oracle_pass("tiny", audios[:1], 1, threads=cores, precision=p) for p in ("fp32", "int8")}
+    probe = {p: cpu_oracle_pass("tiny", audios[:1], 1, threads=cores, precision=p) for p in ("fp32", "int8")}
+    prec = min(probe, key=probe.get)
+    t_start = time.perf_counter()
     for _ in range(min(args.warmup, 1)):  # one warm-up pass builds the weights and pages them in
-        cpu_oracle_pass(args.model, audios, args.beam)
-    t = 0.0
-    for _ in range(args.steps):
-        t += cpu_oracle_pass(args.model, audios, args.beam)
-    audio_s = args.steps * len(audios) * args.seconds
+        cpu_oracle_pass(args.model, audios, args.beam, precision=prec)
+    t, done = 0.0, 0
+    for _ in range(args.steps):  # bounded: a step is one chunk of one stream (~20-40 s for large-v3); stop at the budget
+        t += cpu_oracle_pass(args.model, audios, args.beam, precision=prec)
+        done += 1
+        if time.perf_counter() - t_start > args.cpu_budget_s:
+            break
+    audio_s = done * len(audios) * args.seconds
     value = audio_s / t
     sample = (f"{len(audios)} of {args.streams} streams per step, one {args.seconds:g} s chunk each, "
-              f"full path (log-mel, encoder, beam-{args.beam} decode, word timing), fp32 PyTorch on the host")
+              f"full path (log-mel, encoder, beam-{args.beam} decode, word timing), PyTorch oracle on the host with "
+              f"{prec} Linear layers; {done} of {args.steps} steps timed inside the {args.cpu_budget_s:g} s budget")
     line = {
-        "impl": "reference", "metric": "audio-sec/sec per GPU (RTFx)", "value": value, "unit": "audio-s/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "steps_timed": done, "warmup": args.warmup,
+        "ms_per_step": 1000 * t / done,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8" if prec == "int8" else "f32",
         "data": "synthetic", "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
@@ -193,7 +254,19 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+METRIC = "audio-sec/sec (RTFx), whole job over all GPUs (per_gpu_value = value / n_gpus)"
+
+
 def workload_config(args):
+    if args.config == "small64":
+        return {"workload": f"whisper small bf16, beam {args.beam}, 64 concurrent 16 kHz streams per GPU, each "
+                            f"{args.stream_seconds or 60:g} s of audio submitted in 1 s increments through the batched "
+                            "streaming policy (growing buffers, trimmed at 15 s), word timestamps on "
+                            "(BASELINE.json configs[2])",
+                "streams_per_gpu": 64, "beam_size": args.beam,
+                "weights": "seeded synthetic (peaked transcript circuit), exact architecture",
+                "cache_note": "inputs larger than L2 (0.5 GB of weights, fresh buffers every step)",
+                "parallelism": "independent streams sharded over GPUs, no collective"}
     return {"workload": f"whisper {args.model} bf16, beam {args.beam}, {args.streams} concurrent 16 kHz streams "
                         f"per GPU x {args.seconds:g} s chunk per step, word timestamps on "
                         "(BASELINE.json configs[3] per-GPU share)",
@@ -266,6 +339,134 @@ def latency_leg(local):
             "what": "wall time of one backend transcribe()+ts_words() call on a 1..15 s buffer, host numpy in"}
 
 
+def plugin_leg(model, audios, args, steps, warmup, barrier, max_over_ranks):
+    """e2e through the reference-facing plugin call: one backend object per stream (BatchedASR, the class that sits
+    where the reference builds CustomFasterWhisperASR), one host thread per stream as the reference's loop would be,
+    every step each thread calls asr.transcribe(audio, init_prompt) + asr.ts_words(res)
+    (/root/reference/asr_components.py:267-297) on a HOST numpy buffer; the StreamBatcher gathers the concurrent calls
+    into one batch.  Returns (ms per step, batch-size histogram, words returned in the last step)."""
+    import torch
+    from realtime_whisper_asr_b200.scheduler import BatchedASR, StreamBatcher
+    n = len(audios)
+    batcher = StreamBatcher(model, max_batch=n, max_wait_ms=50)
+    asrs = [BatchedASR("en", batcher, transcribe_kwargs={"beam_size": args.beam, "temperature": 0.0}) for _ in range(n)]
+    go, done = threading.Barrier(n + 1), threading.Barrier(n + 1)
+    words = [0] * n
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(warmup + steps):
+                go.wait()
+                res = asrs[i].transcribe(audios[i], init_prompt="")
+                words[i] = len(asrs[i].ts_words(res))
+                done.wait()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            go.abort()
+            done.abort()
+
+    ts = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(n)]
+    [t.start() for t in ts]
+    try:
+        for _ in range(warmup):
+            go.wait()
+            done.wait()
+        barrier()
+        batcher.batch_sizes.clear()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            go.wait()
+            done.wait()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1000.0
+    except threading.BrokenBarrierError:
+        raise errors[0] if errors else RuntimeError("plugin leg: a stream thread failed")
+    [t.join(timeout=10) for t in ts]
+    hist = {}
+    for b in batcher.batch_sizes:
+        hist[str(b)] = hist.get(str(b), 0) + 1
+    batcher.close()
+    return max_over_ranks(ms) / steps, hist, sum(words)
+
+
+def streaming_leg(model, args, n_streams, seconds, rank, policy="batched"):
+    """Growing-buffer streaming (SURVEY 8d cfg 3/4): every stream receives `seconds` of audio in 1 s increments and
+    re-submits its buffer (trimmed at 15 s on segment boundaries) after every increment.
+      policy "batched": realtime_whisper_asr_b200.streaming.BatchedOnlineASR -- one thread, one transcribe_batch per
+                        increment for all streams (SURVEY 8f N1);
+      policy "threads": one upstream-style OnlineASRProcessor (tests/harness stand-in of whisper_online) per stream on
+                        its own host thread, calls gathered by the StreamBatcher -- the reference's loop, replicated.
+    RTFx per SUBMITTED audio second (every re-submitted buffer second counts: the product's own definition,
+    /root/reference/performance_monitor.py:147-175) and per UNIQUE audio second."""
+    import torch
+    from tests.synth import speech_like
+    auds = [speech_like(777 + rank * 100000 + i, seconds) for i in range(n_streams)]
+    n_inc = int(seconds)
+    kw = {"beam_size": args.beam, "temperature": 0.0}
+    out = {"policy": policy, "streams": n_streams, "seconds_per_stream": seconds, "increments": n_inc}
+    inner = {"s": 0.0}
+    orig = model.transcribe_batch
+
+    def timed(*a, **k):
+        t0 = time.perf_counter()
+        try:
+            return orig(*a, **k)
+        finally:
+            inner["s"] += time.perf_counter() - t0
+
+    model.transcribe_batch = timed
+    try:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if policy == "batched":
+            from realtime_whisper_asr_b200.streaming import BatchedOnlineASR
+            pol = BatchedOnlineASR(model, agreement_n=2, buffer_trimming=("segment", 15), transcribe_kwargs=kw)
+            for i in range(n_streams):
+                pol.add_stream(i, "en")
+            committed = 0
+            for it in range(n_inc):
+                for i in range(n_streams):
+                    pol.insert_audio_chunk(i, auds[i][it * SR:(it + 1) * SR])
+                for _, (b, e, text) in pol.process_iter().items():
+                    committed += len(text)
+            submitted, calls, hist = pol.audio_seconds_submitted, pol.calls, {str(n_streams): pol.calls}
+        else:
+            from realtime_whisper_asr_b200.scheduler import BatchedASR, StreamBatcher
+            from tests import harness
+            harness.install()
+            from whisper_online import OnlineASRProcessor
+            batcher = StreamBatcher(model, max_batch=n_streams, max_wait_ms=50)
+            sub = [0.0] * n_streams
+            com = [0] * n_streams
+
+            def worker(i):
+                asr = BatchedASR("en", batcher, transcribe_kwargs=dict(kw))
+                online = OnlineASRProcessor(asr, buffer_trimming=("segment", 15))
+                for it in range(n_inc):
+                    online.insert_audio_chunk(auds[i][it * SR:(it + 1) * SR])
+                    sub[i] += len(online.audio_buffer) / SR
+                    com[i] += len(online.process_iter()[2])
+
+            ts = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(n_streams)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+            hist = {}
+            for b in batcher.batch_sizes:
+                hist[str(b)] = hist.get(str(b), 0) + 1
+            submitted, calls, committed = sum(sub), batcher.batches_run, sum(com)
+            batcher.close()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    finally:
+        model.transcribe_batch = orig
+    out.update({"wall_s": wall, "backend_calls": calls, "batch_size_histogram": hist,
+                "audio_s_submitted": submitted, "audio_s_unique": n_streams * seconds,
+                "rtfx_submitted": submitted / wall, "rtfx_unique": n_streams * seconds / wall,
+                "host_policy_share": max(0.0, 1.0 - inner["s"] / wall), "committed_chars": committed})
+    return out
+
+
 # ------------------------------------------------------------------------------------ GPU path
 def run_b200(args, rank, world, local):
     import torch
@@ -299,6 +500,19 @@ def run_b200(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(x):
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    if args.config == "small64":
+        run_small64(args, rank, world, local, model, barrier, max_over_ranks, sum_over_ranks)
+        if use_dist:
+            dist.destroy_process_group()
+        return
+
     # ---- device-resident leg: audio uploaded once, outside the timed region
     audio_dev, offsets = FE.upload_audio(audios, dev)
     torch.cuda.synchronize()
@@ -311,6 +525,7 @@ def run_b200(args, rank, world, local):
     launches0 = _lib.launch_count()
     import ctypes as C
     _lib.check(lib.b200w_gemm_profile_begin(256))
+    _lib.check(lib.b200w_attn_profile_begin())
     _lib.check(lib.b200w_step_probe_reset(model.engine._h))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -324,6 +539,8 @@ def run_b200(args, rank, world, local):
     launches = _lib.launch_count() - launches0
     tms, tfl, tn = C.c_double(), C.c_double(), C.c_int64()
     _lib.check(lib.b200w_gemm_profile_end(C.byref(tms), C.byref(tfl), C.byref(tn)))
+    ams, afl, an = C.c_double(), C.c_double(), C.c_int64()
+    _lib.check(lib.b200w_attn_profile_end(C.byref(ams), C.byref(afl), C.byref(an)))
     # one extra, untimed pass with per-phase synchronisation: where the step goes (stderr only)
     model.profile_phases = True
     model.last_timings = {}
@@ -335,17 +552,21 @@ def run_b200(args, rank, world, local):
     n_words = sum(len(s.words) for segs, _ in out for s in segs)
     n_tokens = sum(len(s.tokens) for segs, _ in out for s in segs)
 
-    # ---- end-to-end leg: host numpy in, Python objects out, every step
+    # ---- end-to-end legs.  (1) THE e2e number: the reference-facing plugin call, one backend object and one host
+    # thread per stream, host numpy in, timestamped words out (H2D of every chunk and D2H of the results inside the
+    # timed region).  (2) the same step through one direct transcribe_batch call, for comparison.
+    e2e_ms_step, batch_hist, e2e_words = plugin_leg(model, audios, args, args.steps, max(1, args.warmup // 3), barrier,
+                                                    max_over_ranks)
+    e2e_ms = e2e_ms_step * args.steps
     for _ in range(max(1, args.warmup // 3)):
         model.transcribe_batch(audios, **kw)
     barrier()
-    t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         out2 = model.transcribe_batch(audios, **kw)
     ev1.record()
     barrier()
-    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    direct_ms = max_over_ranks(ev0.elapsed_time(ev1))
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
@@ -378,6 +599,13 @@ def run_b200(args, rank, world, local):
                      "traffic": traffic_of("gemm_traffic.json"), "peak_source": peak_src,
                      "launches_timed": int(tn.value), "kernel_ms_per_step": tms.value / args.steps,
                      "share_of_step": tms.value / dev_ms if dev_ms else None,
+                     "timing": "CUDA events around every launch inside the timed region"}
+    a_ach = (afl.value / 1e12) / (ams.value / 1e3) if ams.value > 0 else None
+    roofline_attn = {"bound": "tensor", "kernel": "enc_attn_kernel", "achieved": a_ach, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (a_ach / peak_tf) if a_ach else None, "traffic": None, "peak_source": peak_src,
+                     "launches_timed": int(an.value), "kernel_ms_per_step": ams.value / args.steps,
+                     "share_of_step": ams.value / dev_ms if dev_ms else None,
+                     "algorithmic_flops_per_launch": (afl.value / an.value) if an.value else None,
                      "timing": "CUDA events around every launch inside the timed region"}
     # ---- decode ops: one extra pass of the same step, decode steps launched eagerly with events per op
     _lib.check(lib.b200w_op_profile_enable(model.engine._h, 1))
@@ -426,39 +654,84 @@ def run_b200(args, rank, world, local):
     if rank != 0:
         return
     line = {
-        "metric": "audio-sec/sec per GPU (RTFx)", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args),
         "per_gpu_value": value / world,
         "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps,
+                "path": "one BatchedASR backend object + host thread per stream: asr.transcribe(host numpy, init_prompt) "
+                        "+ asr.ts_words(), concurrent calls gathered by the StreamBatcher",
+                "batch_size_histogram": batch_hist, "words_per_step": e2e_words},
+        "e2e_transcribe_batch": {"value": audio_s / (direct_ms / 1000.0), "unit": "audio-s/s",
+                                 "ms_per_step": direct_ms / args.steps,
+                                 "path": "one direct model.transcribe_batch(host numpy list) call per step"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": roofline,
         "roofline_gemm": roofline_gemm,
+        "roofline_attn": roofline_attn,
         "decode_ops_ms_per_step": decode_ops,
         "tokens_per_step": n_tokens, "words_per_step": n_words,
     }
     if world == 1 and not args.no_side_legs:
+        try:  # streaming (growing-buffer) workload on the same model: batched policy vs one thread per stream
+            sec = args.stream_seconds or 12.0
+            line["streaming"] = {p: streaming_leg(model, args, args.streams, sec, rank, p) for p in ("batched", "threads")}
+        except Exception as ex:  # side legs must never cost the headline number
+            line["streaming_error"] = repr(ex)
         del model
         torch.cuda.empty_cache()
         try:
             line["frontend"] = frontend_leg(dev, peaks)
             line["latency"] = latency_leg(local)
-        except Exception as ex:  # side legs must never cost the headline number
+        except Exception as ex:
             line["side_leg_error"] = repr(ex)
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        sample_audios = audios[: args.cpu_sample_streams]
-        t = cpu_oracle_pass(args.model, sample_audios, args.beam, threads=cores)
-        line["cpu_baseline"] = {
-            "value": len(sample_audios) * args.seconds / t, "unit": "audio-s/s", "cores": cores, "kind": "port",
-            "sample": f"{len(sample_audios)} of {args.streams} streams, one {args.seconds:g} s chunk, full path, "
-                      f"fp32 PyTorch oracle on the host ({t:.1f} s of CPU work)"}
+        line["cpu_baseline"] = cpu_baseline_report(args, audios)
     print(json.dumps(line), flush=True)
     if use_dist:
         dist.destroy_process_group()
+
+
+def run_small64(args, rank, world, local, model, barrier, max_over_ranks, sum_over_ranks):
+    """BASELINE configs[2]: whisper small, 64 streams per GPU, 60 s of audio per stream in 1 s increments.  One step =
+    one increment of every stream through the batched streaming policy (host buffers in, committed text out)."""
+    import torch
+    from realtime_whisper_asr_b200 import _lib
+    sec = args.stream_seconds or 60.0
+    streaming_leg(model, args, args.streams, 3.0, rank, "batched")  # warm-up: graphs, allocator
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    res = streaming_leg(model, args, args.streams, sec, rank, "batched")
+    barrier()
+    launches = _lib.launch_count() - launches0
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    wall = max_over_ranks(res["wall_s"])
+    submitted = sum_over_ranks(res["audio_s_submitted"])
+    unique = sum_over_ranks(res["audio_s_unique"])
+    threads = streaming_leg(model, args, args.streams, min(sec, 20.0), rank, "threads") if world == 1 else None
+    if rank != 0:
+        return
+    n_inc = res["increments"]
+    line = {
+        "metric": METRIC + "; every re-submitted buffer second counts", "value": submitted / wall, "unit": "audio-s/s",
+        "n_gpus": world, "steps": n_inc, "warmup": 3, "ms_per_step": 1000.0 * wall / n_inc, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+        "per_gpu_value": submitted / wall / world,
+        "rtfx_unique_audio": unique / wall,
+        "e2e": {"value": submitted / wall, "unit": "audio-s/s",
+                "h2d_bytes_per_step": int(4 * SR * res["audio_s_submitted"] / n_inc),
+                "d2h_bytes_per_step": int(args.streams * (448 * 4 + 8 + (448 + 1502) * 8 + 448 * 4)),
+                "path": "BatchedOnlineASR.process_iter (batched streaming policy) over host numpy buffers"},
+        "gpu_launches": int(launches), "clocks": sampler.summary(),
+        "streaming": {"batched": res, "threads": threads},
+    }
+    print(json.dumps(line), flush=True)
 
 
 def main():

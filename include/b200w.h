@@ -56,6 +56,9 @@ int b200w_step_probe_reset(struct b200w_engine* e);
 int b200w_step_probe_read(struct b200w_engine* e, double* total_ms, int64_t* launches, double* bytes);
 int b200w_gemm_profile_begin(int bn);
 int b200w_gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches);
+/* The same for the encoder self-attention kernel (algorithmic flops 4 T^2 d per window and launch). */
+int b200w_attn_profile_begin(void);
+int b200w_attn_profile_end(double* total_ms, double* total_flops, int64_t* launches);
 
 /* ---------------------------------------------------------------- front end (HBM-bound) ------ */
 

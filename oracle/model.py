@@ -14,6 +14,10 @@ Two precisions:
           faster-whisper's compute_type="bfloat16" stores between CTranslate2 ops, and it is the
           precision contract the token-exactness tests hold the CUDA path to.  The residual stream
           and LayerNorm statistics stay in fp32.
+  "int8"  CPU-baseline variant only (bench.py), never a parity reference: every Linear layer (and the tied output
+          projection) runs as CTranslate2's int8 CPU path does -- weights quantised to int8 per output
+          row, activations quantised dynamically per call, s8 x s8 -> s32 GEMM (torch's quantized.linear_dynamic on
+          the x86 / fbgemm engine) -- with conv, LayerNorm, softmax and GELU in fp32.
 State-dict keys follow OpenAI Whisper (encoder.blocks.0.attn.query.weight, ...).
 """
 from __future__ import annotations
@@ -55,14 +59,30 @@ def _bf(x: torch.Tensor) -> torch.Tensor:
 
 class OracleWhisper:
     def __init__(self, sd: Dict[str, torch.Tensor], dims: Dims, precision: str = "fp32"):
-        assert precision in ("fp32", "bf16")
+        assert precision in ("fp32", "bf16", "int8")
         self.sd = {k: v.to(torch.float32) for k, v in sd.items()}
         self.dims = dims
         self.precision = precision
         self.r = _bf if precision == "bf16" else (lambda x: x)
+        self._packed = {}  # int8: prefix -> prepacked (per-row int8 weight, fp32 bias)
+
+    def _int8_linear(self, x, prefix, bias=True):
+        pk = self._packed.get((prefix, bias))
+        if pk is None:
+            w = self.sd[prefix + ".weight"]
+            b = self.sd.get(prefix + ".bias") if bias else None
+            scales = (w.abs().amax(dim=1) / 127.0).clamp_min(1e-12)
+            qw = torch.quantize_per_channel(w, scales, torch.zeros(w.shape[0], dtype=torch.int64), 0, torch.qint8)
+            pk = torch.ops.quantized.linear_prepack(qw, b)
+            self._packed[(prefix, bias)] = pk
+        shp = x.shape
+        y = torch.ops.quantized.linear_dynamic(x.reshape(-1, shp[-1]).contiguous(), pk)
+        return y.reshape(*shp[:-1], y.shape[-1])
 
     # ------------------------------------------------------------------ helpers
     def _lin(self, x, prefix, bias=True):
+        if self.precision == "int8":
+            return self._int8_linear(x, prefix, bias)
         w = self.sd[prefix + ".weight"]
         b = self.sd.get(prefix + ".bias") if bias else None
         return F.linear(x, w, b)
@@ -192,6 +212,8 @@ class OracleWhisper:
 
     def logits(self, hidden: torch.Tensor) -> torch.Tensor:
         h = self.r(self._ln(hidden, "decoder.ln"))
+        if self.precision == "int8":
+            return self._int8_linear(h, "decoder.token_embedding", bias=False)
         return h @ self.sd["decoder.token_embedding.weight"].T
 
     def teacher_forced_logits(self, tokens: List[int], enc_row: torch.Tensor, want_cross_weights=False):

@@ -49,6 +49,8 @@ SIGNATURES = {
     "b200w_step_probe_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "b200w_gemm_profile_begin": (_i, [_i]),
     "b200w_gemm_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "b200w_attn_profile_begin": (_i, []),
+    "b200w_attn_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "b200w_logmel": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "b200w_pack_windows": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "b200w_dedup_features": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

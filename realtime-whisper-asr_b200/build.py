@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200whisper.so")
-SOURCES = ["api.cu", "gemm.cu", "skinny.cu", "attention.cu", "frontend.cu", "kernels.cu", "engine.cu"]
+SOURCES = ["api.cu", "gemm.cu", "skinny.cu", "dstep.cu", "attention.cu", "frontend.cu", "kernels.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

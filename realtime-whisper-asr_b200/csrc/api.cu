@@ -10,6 +10,7 @@
 
 #include "attention.h"
 #include "common.h"
+#include "dstep.h"
 #include "frontend.h"
 #include "gemm.h"
 #include "skinny.h"
@@ -64,7 +65,8 @@ int b200w_abi_version(void) { return B200W_ABI_VERSION; }
 uint64_t b200w_launch_count(void) { return g_launch_count.load(); }
 
 int b200w_gemm_set_trace(void* dev_buf) {
-  if (getenv("B200W_TRACE_CROSS")) cross_tc_set_trace(dev_buf);
+  if (getenv("B200W_TRACE_DSTEP")) dstep_set_trace(dev_buf, atoi(getenv("B200W_TRACE_DSTEP")));
+  else if (getenv("B200W_TRACE_CROSS")) cross_tc_set_trace(dev_buf);
   else if (getenv("B200W_TRACE_SKINNY")) skinny_set_trace(dev_buf);
   else gemm_set_trace(dev_buf);
   return 0;
@@ -79,6 +81,19 @@ int b200w_gemm_profile_end(double* total_ms, double* total_flops, int64_t* launc
   B200W_API_BEGIN
   long long n = 0;
   gemm_profile_end(total_ms, total_flops, &n);
+  *launches = n;
+  B200W_API_END
+}
+
+int b200w_attn_profile_begin(void) {
+  B200W_API_BEGIN
+  enc_attention_profile_begin();
+  B200W_API_END
+}
+int b200w_attn_profile_end(double* total_ms, double* total_flops, int64_t* launches) {
+  B200W_API_BEGIN
+  long long n = 0;
+  enc_attention_profile_end(total_ms, total_flops, &n);
   *launches = n;
   B200W_API_END
 }

@@ -14,6 +14,9 @@
 //    (query, 4 heads), page-table row staged in shared memory, value rows prefetched to L2 during the
 //    key pass.  Latency-bound CUDA-core work.
 #include "attention.h"
+#include <atomic>
+#include <deque>
+#include <mutex>
 
 #include "gemm.h"
 #include "ptx.cuh"
@@ -243,6 +246,49 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// ---- optional per-launch timing of the encoder attention (bench.py's second tensor roofline): CUDA events around
+// every launch on the launching stream, read back after a synchronize.
+struct AttnProfSlot {
+  cudaEvent_t beg, end;
+  double flops;
+};
+static std::atomic<int> g_attn_prof_on{0};
+static std::deque<AttnProfSlot> g_attn_prof_slots;  // guarded by g_attn_prof_mu
+static size_t g_attn_prof_used = 0;
+static std::mutex g_attn_prof_mu;
+void enc_attention_profile_begin() {
+  std::lock_guard<std::mutex> lock(g_attn_prof_mu);
+  g_attn_prof_on = 1;
+  g_attn_prof_used = 0;
+}
+void enc_attention_profile_end(double* total_ms, double* total_flops, long long* launches) {
+  std::lock_guard<std::mutex> lock(g_attn_prof_mu);
+  g_attn_prof_on = 0;
+  double ms = 0, fl = 0;
+  for (size_t i = 0; i < g_attn_prof_used; ++i) {
+    float t = 0.f;
+    B200W_CHECK_CUDA(cudaEventSynchronize(g_attn_prof_slots[i].end));
+    B200W_CHECK_CUDA(cudaEventElapsedTime(&t, g_attn_prof_slots[i].beg, g_attn_prof_slots[i].end));
+    ms += t;
+    fl += g_attn_prof_slots[i].flops;
+  }
+  *total_ms = ms;
+  *total_flops = fl;
+  *launches = (long long)g_attn_prof_used;
+}
+static AttnProfSlot* attn_prof_slot(double flops) {
+  std::lock_guard<std::mutex> lock(g_attn_prof_mu);
+  if (g_attn_prof_used == g_attn_prof_slots.size()) {
+    AttnProfSlot s;
+    B200W_CHECK_CUDA(cudaEventCreate(&s.beg));
+    B200W_CHECK_CUDA(cudaEventCreate(&s.end));
+    g_attn_prof_slots.push_back(s);
+  }
+  AttnProfSlot* s = &g_attn_prof_slots[g_attn_prof_used++];
+  s->flops = flops;
+  return s;
+}
+
 template <int KT, int CTAS>
 static void launch_enc_attn(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out, cudaStream_t stream) {
   CUtensorMap tmQ, tmKV;
@@ -251,7 +297,13 @@ static void launch_enc_attn(const bf16* qkv, int B, int T, int d, int n_heads, b
   constexpr int smem_bytes = TILE_BYTES + 2 * KT * HD * 2 + 128 * KT * 2 + 5 * 8 + 16 + 1024;
   ensure_dynamic_smem(enc_attn_kernel<KT, CTAS>, smem_bytes);
   EncAttnParams p{T, d, 0.125f * 1.4426950408889634f, out, nullptr, nullptr, nullptr, 0, 0, n_heads};
+  AttnProfSlot* ps = nullptr;
+  if (g_attn_prof_on.load(std::memory_order_relaxed)) {
+    ps = attn_prof_slot(4.0 * (double)T * (double)T * (double)d * (double)B);  // S = Q K^T and O = P V: 2 x 2 T^2 d
+    B200W_CHECK_CUDA(cudaEventRecord(ps->beg, stream));
+  }
   enc_attn_kernel<KT, CTAS><<<dim3(cdiv(T, QT), n_heads, B), 128, smem_bytes, stream>>>(tmQ, tmKV, p);
+  if (ps) B200W_CHECK_CUDA(cudaEventRecord(ps->end, stream));
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }

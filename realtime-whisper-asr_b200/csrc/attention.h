@@ -8,6 +8,10 @@ namespace b200w {
 // 64 inside each third) -> out bf16 [B][T][d].  softmax(q k^T / 8) v, non-causal.
 void enc_attention(const bf16* qkv, int B, int T, int d, int n_heads, bf16* out, cudaStream_t stream);
 
+// Per-launch CUDA-event timing of the encoder attention (algorithmic flops 4 T^2 d per window); see bench.py.
+void enc_attention_profile_begin();
+void enc_attention_profile_end(double* total_ms, double* total_flops, long long* launches);
+
 // Decoder attention for a handful of queries; one warp per (query, head).
 struct DecAttnParams {
   const bf16* q = nullptr;   // query i, head h at q + i * q_stride + h * 64

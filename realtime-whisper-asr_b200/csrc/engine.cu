@@ -22,6 +22,7 @@
 
 #include "attention.h"
 #include "common.h"
+#include "dstep.h"
 #include "gemm.h"
 #include "kernels.h"
 #include "skinny.h"
@@ -203,6 +204,7 @@ struct b200w_engine {
   OpTimer optimer;        // per-op event timing of eager decode passes (profiling aid)
   std::mutex mu;          // one host thread at a time inside an engine call (workspaces are per engine)
   SkinnyCache* skinny_cache = nullptr;  // launch records of this engine's decode-step GEMMs (freed with it)
+  DstepCache* dstep_cache = nullptr;    // records + grid-barrier words of the fused decode-step segments
 };
 
 namespace {
@@ -621,6 +623,123 @@ void logits_for_rows(b200w_engine* e, const int* sel_rows_dev, int n_sel, cudaSt
   }
 }
 
+// ----------------------------------------------------------------------------------- fused decode step
+// Decode steps with the segments between the attentions fused into persistent program kernels (dstep.cu):
+//   K0            [embed, LN1, QKV]                                  (layer 0)
+//   per layer     qkv_attention (split-K reduce + cache write + self-attention)
+//                 A [out, LN2, cq, finalize]
+//                 cross_attention_tc
+//                 B [cout, LN3, fc1, GELU finalize, fc2] + ([LN1, QKV] of the next layer | [final LN, logits])
+// 4 launches per layer instead of 13; same split factors, k ranges and summation orders as the launch-per-op path.
+static bool use_fused_step() {
+  // Opt-in (B200W_DSTEP=1).  Measured on the bench workload (profiles/r02_dstep_fused.txt): identical tokens, but
+  // 5.6 ms per decode step against 3.97 ms for the launch-per-op step -- a software grid barrier costs ~3.3 us
+  // (store drain + atomic + poll) where a PDL-chained launch costs ~1.5-2 us, so fusing removes no latency.
+  static const bool on = getenv("B200W_DSTEP") != nullptr && atoi(getenv("B200W_DSTEP")) != 0;
+  return on;
+}
+static bool fused_step_ok(const b200w_engine* e, int n) {
+  return use_fused_step() && use_skinny() && e->d % 128 == 0 && e->H % 4 == 0 && dstep_supported(n, e->d) &&
+         (size_t)16 * n * e->d * 4 <= e->d_split.bytes && n <= e->logit_rows;
+}
+
+void decoder_step_fused(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, const int* table, int max_kvlen,
+                        cudaStream_t s) {
+  const int n = m.n, d = e->d;
+  float* x = e->d_x.as<float>();
+  bf16* h = e->d_h.as<bf16>();
+  bf16* attn = e->d_attn.as<bf16>();
+  bf16* cq = e->d_cq.as<bf16>();
+  bf16* mlp = e->d_mlp.as<bf16>();
+  bf16* hsel = e->d_hsel.as<bf16>();
+  float* S = e->d_split.as<float>();
+  DsPhaseDesc ph[DS_MAX_PHASES];
+  auto reset = [&]() {
+    memset(static_cast<void*>(ph), 0, sizeof(ph));
+    for (auto& p : ph) { p.rows = n; p.splits = 1; }
+  };
+  auto gemm = [&](DsPhaseDesc& p, const bf16* X, const Lin& l, int N, int K, int max_splits) {
+    p.type = DS_GEMM; p.X = X; p.W = l.w; p.N = N; p.K = K;
+    p.splits = std::max(2, skinny_suggest_splits(N, K, max_splits));
+    p.slabs = S; p.ldo = N;
+    return p.splits;
+  };
+  auto ln = [&](DsPhaseDesc& p, const Norm& nm, int n_slabs, const float* bias, bf16* y) {
+    p.type = DS_LN; p.x = x; p.gamma = nm.g; p.beta = nm.b; p.y = y; p.d = d;
+    p.n_slabs = n_slabs; p.slabs = n_slabs ? S : nullptr; p.bias = n_slabs ? bias : nullptr;
+  };
+  auto fin = [&](DsPhaseDesc& p, int n_slabs, const float* bias, int N, int act, bf16* out) {
+    p.type = DS_FIN; p.slabs = S; p.n_slabs = n_slabs; p.bias = bias; p.N = N; p.act = act; p.out = out;
+  };
+  // K0: embedding, first LayerNorm, first QKV projection
+  int qkv_splits;
+  RUN(2) {
+    OP(2);
+    reset();
+    ph[0].type = DS_EMBED; ph[0].tok = m.tok; ph[0].pos = m.pos; ph[0].tok_emb = e->tok_emb; ph[0].pos_emb = e->dec_pos;
+    ph[0].x = x; ph[0].d = d;
+    ln(ph[1], e->dec[0].ln1, 0, nullptr, h);
+    qkv_splits = gemm(ph[2], h, e->dec[0].qkv, 3 * d, d, 4);
+    dstep_run(e->dstep_cache, 128 * n, ph, 3, s);
+  }
+  qkv_splits = std::max(2, skinny_suggest_splits(3 * d, d, 4));
+  for (int l = 0; l < e->Ld; ++l) {
+    const DecLayer& L = e->dec[l];
+    bf16* kp = e->kpool.as<bf16>() + (long long)l * e->total_slots * d;
+    bf16* vp = e->vpool.as<bf16>() + (long long)l * e->total_slots * d;
+    RUN(4) {
+      OP(4);
+      QkvAttnParams qa;
+      qa.partial = S; qa.n_splits = qkv_splits; qa.split_stride = (long long)n * 3 * d; qa.bias = L.qkv.b; qa.d = d;
+      qa.slot = m.slot; qa.kpool = kp; qa.vpool = vp;
+      qa.table = table; qa.table_stride = e->Tctx; qa.trow = m.trow; qa.kvlen = m.kvlen;
+      qa.out = attn; qa.out_stride = d; qa.scale = 0.125f; qa.max_len = max_kvlen;
+      qkv_attention(qa, n, e->H, s);
+    }
+    RUN(6) {
+      OP(6);
+      reset();
+      const int so = gemm(ph[0], attn, L.out, d, d, 7);
+      ln(ph[1], L.ln2, so, L.out.b, h);
+      const int sq = gemm(ph[2], h, L.cq, d, d, 7);
+      fin(ph[3], sq, L.cq.b, d, 0, cq);
+      dstep_run(e->dstep_cache, 128 * n + 1 + 2 * l, ph, 4, s);
+    }
+    RUN(7) {
+      e->optimer.next_work = (double)m.n_live_host * e->H * 2.0 * e->Tenc * HEAD_DIM * 2.0;
+      OpScope _op_scope_x(e->optimer, 7, s);
+      const bool probe = l == e->Ld / 2 && !e->optimer.on;
+      if (probe) probe_record(e->xev0, s);
+      cross_attention_tc(cross_kv, e->cfg.max_batch, e->Ld, l, e->H, e->Tenc, cq, d, m.stream, m.g_start, m.g_count,
+                         m.n_live, m.n_groups, attn, d, 0.125f, e->x_tc.p, s, cross_step_pieces());
+      if (probe) { probe_record(e->xev1, s); e->xev_recorded = true; }
+    }
+    RUN(9) {
+      OP(9);
+      reset();
+      const int sc = gemm(ph[0], attn, L.cout, d, d, 7);
+      ln(ph[1], L.ln3, sc, L.cout.b, h);
+      const int s1 = gemm(ph[2], h, L.fc1, 4 * d, d, 3);
+      fin(ph[3], s1, L.fc1.b, 4 * d, 1, mlp);
+      const int s2 = gemm(ph[4], mlp, L.fc2, d, 4 * d, 10);
+      if (l + 1 < e->Ld) {
+        ln(ph[5], e->dec[l + 1].ln1, s2, L.fc2.b, h);
+        gemm(ph[6], h, e->dec[l + 1].qkv, 3 * d, d, 4);
+      } else {  // final LayerNorm + tied-embedding logits (one slab = the logits buffer itself, row stride ldv)
+        ln(ph[5], e->dec_ln, s2, L.fc2.b, hsel);
+        Lin emb;
+        emb.w = e->tok_emb;
+        gemm(ph[6], hsel, emb, e->V, d, 1);
+        ph[6].splits = 1;
+        ph[6].slabs = e->logits.as<float>();
+        ph[6].ldo = e->ldv;
+      }
+      dstep_run(e->dstep_cache, 128 * n + 2 + 2 * l, ph, 7, s);
+    }
+  }
+  e->pending = SplitReduce{};
+}
+
 void upload_ints(int* dst, const std::vector<int>& v, cudaStream_t s) {
   if (v.empty()) return;
   B200W_CHECK_CUDA(cudaMemcpyAsync(dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice, s));
@@ -644,6 +763,7 @@ int b200w_engine_create(const b200w_model_config* cfg, b200w_engine** out) {
   b200w_engine* e = new b200w_engine();
   e->cfg = *cfg;
   e->skinny_cache = skinny_cache_create();
+  e->dstep_cache = dstep_cache_create();
   e->d = cfg->d_model; e->H = cfg->n_heads; e->Le = cfg->n_enc_layers; e->Ld = cfg->n_dec_layers;
   e->V = cfg->n_vocab; e->ldv = (cfg->n_vocab + 7) / 8 * 8; e->Tctx = cfg->n_text_ctx; e->Tenc = cfg->n_audio_ctx;
   *out = e;
@@ -664,6 +784,7 @@ int b200w_engine_destroy(b200w_engine* e) {
     cudaDeviceSynchronize();  // nothing of this engine may still be in flight
     for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.exec);
     skinny_cache_destroy(e->skinny_cache);
+    dstep_cache_destroy(e->dstep_cache);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->join_event) cudaEventDestroy(e->join_event);
     if (e->xev0) cudaEventDestroy(e->xev0);
@@ -1036,8 +1157,12 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
                        m.n, Tctx, s);
     e->step_pass = true;
     try {
-      decoder_forward(e, ckv, m, e->tables[from ^ 1].as<int>(), Tctx, nullptr, s);
-      logits_for_rows(e, nullptr, m.n, s);
+      if (fused_step_ok(e, m.n) && m.max_group <= CROSS_GROUP && m.n_groups <= 64) {
+        decoder_step_fused(e, ckv, m, e->tables[from ^ 1].as<int>(), Tctx, s);
+      } else {
+        decoder_forward(e, ckv, m, e->tables[from ^ 1].as<int>(), Tctx, nullptr, s);
+        logits_for_rows(e, nullptr, m.n, s);
+      }
     } catch (...) {
       e->step_pass = false;
       throw;

@@ -9,7 +9,8 @@ stream's buffer and prompt, so
     max-over-ranks of timings (NCCL on GPUs, gloo in the CPU tests);
   * inside a GPU concurrent calls are BATCHED: ``StreamBatcher`` gathers the calls that arrive
     within a short window and runs them as one ``transcribe_batch`` (one encoder / decoder / align
-    launch sequence for all of them), each caller getting exactly what a solo call would return.
+    launch sequence for all of them), each caller getting exactly what a solo call would return (every kernel on
+    the path is batch-invariant: tests/test_gpu_fullsize.py::test_batch_invariance_full_size).
 ``BatchedASR`` is a ``B200WhisperASR`` whose ``transcribe`` goes through the batcher, so several
 stream processors (one thread each, as the reference's loop would be per stream) share one engine.
 """
@@ -77,6 +78,8 @@ class StreamBatcher:
         self._stop = False
         self.batches_run = 0
         self.requests_run = 0
+        self.batch_sizes: List[int] = []      # size of every batch run (bench.py's histogram)
+        self.busy_seconds = 0.0               # wall time spent inside model.transcribe_batch
         self._thread = threading.Thread(target=self._loop, name="b200w-batcher", daemon=True)
         self._thread.start()
 
@@ -124,6 +127,7 @@ class StreamBatcher:
             batch = self._take_batch()
             if not batch:
                 return
+            t0 = time.perf_counter()
             try:
                 out = self.model.transcribe_batch([r.audio for r in batch], languages=[r.language for r in batch],
                                                   initial_prompts=[r.initial_prompt for r in batch], **batch[0].kwargs)
@@ -132,8 +136,10 @@ class StreamBatcher:
             except BaseException as e:  # delivered to every caller of the batch, as a solo call would raise
                 for r in batch:
                     r.error = e
+            self.busy_seconds += time.perf_counter() - t0
             self.batches_run += 1
             self.requests_run += len(batch)
+            self.batch_sizes.append(len(batch))
             for r in batch:
                 r.done.set()
 
