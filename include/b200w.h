@@ -91,6 +91,16 @@ int b200w_dedup_features(const float* audio_dev, const int64_t* offsets_dev, int
                          int max_points, int sample_rate, float* out_dev, float* raw_out_dev,
                          void* stream);
 
+/* Band-pass pre-filter of n_chunks chunks: scipy.signal.filtfilt(b, a, chunk) with scipy's defaults (odd extension
+ * by 27 samples, steady-state initial conditions) for an 8th-order IIR -- what the reference applies to every
+ * incoming chunk (/root/reference/vocal_separation.py:335-365 SimpleFilterSeparator.separate: 4th-order Butterworth
+ * band-pass 85-3400 Hz; call site 一键实时识别麦克风.py:1474-1482).
+ *   coeffs_host  26 doubles (HOST memory): b[9], a[9] with a[0] == 1, zi[8] (scipy.signal.lfilter_zi)
+ *   out_dev      fp32, same layout as audio_dev       scratch_dev  fp32 [n_chunks][27]
+ * Chunks of <= 27 samples are copied unchanged (scipy refuses them; the reference then keeps the original audio). */
+int b200w_bandpass_filtfilt(const float* audio_dev, const int64_t* offsets_dev, int n_chunks,
+                            const double* coeffs_host, float* out_dev, float* scratch_dev, void* stream);
+
 /* ---------------------------------------------------------------- building blocks (tests) ---- */
 
 /* out[M][N] = act(A[M][K] * W[N][K]^T + bias) + residual.  bf16 operands, fp32 accumulate on

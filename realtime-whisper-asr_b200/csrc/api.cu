@@ -130,6 +130,15 @@ int b200w_dedup_features(const float* audio_dev, const int64_t* offsets_dev, int
   B200W_API_END
 }
 
+int b200w_bandpass_filtfilt(const float* audio_dev, const int64_t* offsets_dev, int n_chunks,
+                            const double* coeffs_host, float* out_dev, float* scratch_dev, void* stream) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(audio_dev && offsets_dev && coeffs_host && out_dev && scratch_dev, "null argument");
+  bandpass_filtfilt_launch(audio_dev, reinterpret_cast<const long long*>(offsets_dev), n_chunks, coeffs_host, out_dev,
+                           scratch_dev, static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
 int b200w_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev,
                     const void* residual_dev, void* out_dev, int M, int N, int K, int64_t lda,
                     int64_t ldw, int64_t ldr, int64_t ldo, int flags, int force_bn, void* stream) {

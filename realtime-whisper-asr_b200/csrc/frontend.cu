@@ -724,4 +724,138 @@ void dedup_features_launch(const float* audio, const long long* offsets, int n_c
   B200W_CHECK_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------- band-pass pre-filter
+// Zero-phase IIR band-pass of every chunk: scipy.signal.filtfilt(b, a, x) with its defaults (odd extension by
+// padlen = 3 * max(len(a), len(b)) samples at both ends, steady-state initial conditions zi * first sample, forward
+// pass, time-reversed pass), which the reference applies to each incoming chunk before the dedup check and the ASR
+// buffer (SimpleFilterSeparator.separate, /root/reference/vocal_separation.py:335-365: 4th-order Butterworth,
+// 85-3400 Hz, i.e. 9 + 9 coefficients; call site 一键实时识别麦克风.py:1474-1482).
+// The recurrence is sequential in time, chunks are independent: one thread per chunk, 128 chunks per CTA; the samples
+// go through shared memory in 32-sample pieces so that global traffic is coalesced (a warp moves one chunk's 128
+// bytes per instruction) although a thread walks its chunk serially.  Arithmetic in fp64 registers (direct form II
+// transposed, the same structure scipy's lfilter uses), storage fp32.  Forward pass writes y into `out`, the
+// reversed pass rewrites it in place (position i only depends on y[i..]).  Chunks not longer than padlen are passed
+// through unchanged (scipy raises there, the reference catches it and keeps the original audio).
+static constexpr int BP_ORDER = 8;            // len(a) - 1 for the 4th-order band-pass
+static constexpr int BP_PAD = 3 * (BP_ORDER + 1);
+static constexpr int BP_CHUNKS = 128;         // chunks (= threads) per CTA
+static constexpr int BP_PIECE = 32;           // samples per chunk per staged piece
+struct BandpassCoeffs {
+  double b[BP_ORDER + 1], a[BP_ORDER + 1], zi[BP_ORDER];
+};
+struct BandpassArgs {
+  const float* x;
+  const long long* offsets;  // [n_chunks + 1]
+  float* out;
+  float* rpad;               // [n_chunks][BP_PAD] forward-pass outputs over the right extension
+  int n_chunks;
+};
+
+__device__ __forceinline__ double bp_step(double xin, double (&z)[BP_ORDER], const BandpassCoeffs& c) {
+  const double y = fma(c.b[0], xin, z[0]);
+#pragma unroll
+  for (int i = 0; i < BP_ORDER - 1; ++i) z[i] = fma(c.b[i + 1], xin, fma(-c.a[i + 1], y, z[i + 1]));
+  z[BP_ORDER - 1] = fma(c.b[BP_ORDER], xin, -c.a[BP_ORDER] * y);
+  return y;
+}
+
+__global__ void __launch_bounds__(BP_CHUNKS) bandpass_filtfilt_kernel(const BandpassArgs g, const BandpassCoeffs c) {
+  __shared__ float tile[BP_CHUNKS][BP_PIECE + 1];
+  __shared__ float hist[BP_CHUNKS][BP_PAD + 2];  // last BP_PAD + 1 inputs of every chunk (circular)
+  __shared__ long long s_off[BP_CHUNKS + 1];
+  __shared__ int s_maxn;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int c0 = blockIdx.x * BP_CHUNKS;
+  const int nc = min(BP_CHUNKS, g.n_chunks - c0);
+  if (t == 0) s_maxn = 0;
+  for (int i = t; i <= nc; i += BP_CHUNKS) s_off[i] = g.offsets[c0 + i];
+  __syncthreads();
+  const long long off = t < nc ? s_off[t] : 0;
+  const int N = t < nc ? (int)(s_off[t + 1] - s_off[t]) : 0;
+  atomicMax(&s_maxn, N);
+  __syncthreads();
+  const int maxn = s_maxn;
+  const bool filt = N > BP_PAD;  // shorter chunks: passthrough
+  double z[BP_ORDER];
+  // ---------------- forward pass
+  const int n_pieces = (maxn + BP_PIECE - 1) / BP_PIECE;
+  for (int p = 0; p < n_pieces; ++p) {
+    for (int r = warp; r < nc; r += BP_CHUNKS / 32) {  // coalesced: one warp, one chunk row
+      const int n = (int)(s_off[r + 1] - s_off[r]), i = p * BP_PIECE + lane;
+      tile[r][lane] = i < n ? g.x[s_off[r] + i] : 0.f;
+    }
+    __syncthreads();
+    if (t < nc) {
+      const int base = p * BP_PIECE;
+      if (filt && p == 0) {
+        // left extension 2 x[0] - x[BP_PAD - i], i = 0 .. BP_PAD-1 (N > BP_PAD >= piece 0 holds x[1..27])
+        const double x0 = tile[t][0];
+        const double e0 = 2.0 * x0 - (double)tile[t][BP_PAD];
+#pragma unroll
+        for (int i = 0; i < BP_ORDER; ++i) z[i] = c.zi[i] * e0;
+        for (int i = 0; i < BP_PAD; ++i) bp_step(2.0 * x0 - (double)tile[t][BP_PAD - i], z, c);
+      }
+      const int cnt = min(BP_PIECE, N - base);
+      for (int i = 0; i < cnt; ++i) {
+        const float xv = tile[t][i];
+        hist[t][(base + i) % (BP_PAD + 2)] = xv;
+        tile[t][i] = filt ? (float)bp_step((double)xv, z, c) : xv;
+      }
+      if (filt && cnt > 0 && base + cnt == N) {
+        // right extension 2 x[N-1] - x[N-2-j]: forward outputs kept for the start of the reversed pass
+        const double xl = hist[t][(N - 1) % (BP_PAD + 2)];
+        float* rp = g.rpad + (long long)(c0 + t) * BP_PAD;
+        for (int j = 0; j < BP_PAD; ++j) rp[j] = (float)bp_step(2.0 * xl - (double)hist[t][(N - 2 - j) % (BP_PAD + 2)], z, c);
+      }
+    }
+    __syncthreads();
+    for (int r = warp; r < nc; r += BP_CHUNKS / 32) {
+      const int n = (int)(s_off[r + 1] - s_off[r]), i = p * BP_PIECE + lane;
+      if (i < n) g.out[s_off[r] + i] = tile[r][lane];
+    }
+    __syncthreads();
+  }
+  // ---------------- reversed pass over [right extension, y[N-1] .. y[0]] (the left extension's outputs are dropped)
+  if (filt) {
+    const float* rp = g.rpad + (long long)(c0 + t) * BP_PAD;
+    const double e0 = rp[BP_PAD - 1];
+#pragma unroll
+    for (int i = 0; i < BP_ORDER; ++i) z[i] = c.zi[i] * e0;
+    for (int j = BP_PAD - 1; j >= 0; --j) bp_step((double)rp[j], z, c);
+  }
+  for (int p = n_pieces - 1; p >= 0; --p) {
+    for (int r = warp; r < nc; r += BP_CHUNKS / 32) {
+      const int n = (int)(s_off[r + 1] - s_off[r]), i = p * BP_PIECE + lane;
+      tile[r][lane] = i < n ? g.out[s_off[r] + i] : 0.f;
+    }
+    __syncthreads();
+    if (t < nc && filt) {
+      const int base = p * BP_PIECE;
+      const int cnt = min(BP_PIECE, N - base);
+      for (int i = cnt - 1; i >= 0; --i) tile[t][i] = (float)bp_step((double)tile[t][i], z, c);
+    }
+    __syncthreads();
+    for (int r = warp; r < nc; r += BP_CHUNKS / 32) {
+      const int n = (int)(s_off[r + 1] - s_off[r]), i = p * BP_PIECE + lane;
+      if (i < n) g.out[s_off[r] + i] = tile[r][lane];
+    }
+    __syncthreads();
+  }
+  (void)off;
+}
+
+void bandpass_filtfilt_launch(const float* audio, const long long* offsets, int n_chunks, const double* coeffs_host,
+                              float* out, float* rpad_scratch, cudaStream_t stream) {
+  if (n_chunks <= 0) return;
+  BandpassCoeffs c;
+  memcpy(c.b, coeffs_host, sizeof(double) * (BP_ORDER + 1));
+  memcpy(c.a, coeffs_host + BP_ORDER + 1, sizeof(double) * (BP_ORDER + 1));
+  memcpy(c.zi, coeffs_host + 2 * (BP_ORDER + 1), sizeof(double) * BP_ORDER);
+  B200W_REQUIRE(fabs(c.a[0] - 1.0) < 1e-12, "bandpass_filtfilt: a[0] must be 1 (normalised coefficients)");
+  BandpassArgs g{audio, offsets, out, rpad_scratch, n_chunks};
+  bandpass_filtfilt_kernel<<<cdiv(n_chunks, BP_CHUNKS), BP_CHUNKS, 0, stream>>>(g, c);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
 }  // namespace b200w

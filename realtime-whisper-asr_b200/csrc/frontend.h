@@ -20,4 +20,10 @@ void dedup_features_launch(const float* audio, const long long* offsets, int n_c
                            int max_points, int sample_rate, float* out, float* raw_out,
                            cudaStream_t stream);
 
+// Zero-phase 8th-order IIR (scipy.signal.filtfilt defaults) of every chunk.  coeffs_host: b[9], a[9] (a[0] = 1),
+// zi[8] as doubles.  rpad_scratch: [n_chunks][27] floats.  Chunks of <= 27 samples are copied unchanged.
+void bandpass_filtfilt_launch(const float* audio, const long long* offsets, int n_chunks, const double* coeffs_host,
+                              float* out, float* rpad_scratch, cudaStream_t stream);
+static constexpr int BANDPASS_PAD = 27;
+
 }  // namespace b200w

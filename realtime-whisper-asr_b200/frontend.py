@@ -151,3 +151,72 @@ def dedup_features(audio_dev: torch.Tensor, offsets: np.ndarray, sample_rate: in
                                         raw.data_ptr() if raw is not None else None,
                                         _stream_ptr(device)))
     return (out, raw) if return_raw else out
+
+
+# ----------------------------------------------------------------------------------- band-pass pre-filter
+def butter_bandpass(order: int, low_hz: float, high_hz: float, sample_rate: int = SAMPLE_RATE):
+    """Digital Butterworth band-pass as (b, a) float64 -- scipy.signal.butter(order, [low, high], btype='band') with
+    normalised edges low/(sr/2), high/(sr/2): analog low-pass prototype poles, low-pass -> band-pass transform,
+    bilinear transform (fs = 2, pre-warped edges), polynomial expansion.  2*order + 1 coefficients each."""
+    nyq = sample_rate / 2.0
+    wn = np.array([low_hz / nyq, high_hz / nyq], dtype=np.float64)
+    if not (0.0 < wn[0] < wn[1] < 1.0):
+        raise ValueError("band edges must satisfy 0 < low < high < sample_rate / 2")
+    fs = 2.0
+    warped = 2.0 * fs * np.tan(np.pi * wn / fs)
+    bw, wo = warped[1] - warped[0], np.sqrt(warped[0] * warped[1])
+    m = np.arange(-order + 1, order, 2)
+    p_lp = -np.exp(1j * np.pi * m / (2 * order))            # prototype poles (no zeros, gain 1)
+    p_s = p_lp * bw / 2.0
+    p_bp = np.concatenate([p_s + np.sqrt(p_s ** 2 - wo ** 2), p_s - np.sqrt(p_s ** 2 - wo ** 2)])
+    z_bp = np.zeros(order)                                  # `order` zeros at the origin
+    k_bp = bw ** order
+    fs2 = 2.0 * fs
+    z_d = (fs2 + z_bp) / (fs2 - z_bp)
+    p_d = (fs2 + p_bp) / (fs2 - p_bp)
+    z_d = np.append(z_d, -np.ones(len(p_bp) - len(z_bp)))   # zeros at infinity map to z = -1
+    k_d = k_bp * np.real(np.prod(fs2 - z_bp) / np.prod(fs2 - p_bp))
+    b = k_d * np.real(np.poly(z_d))
+    a = np.real(np.poly(p_d))
+    return b.astype(np.float64), a.astype(np.float64)
+
+
+def lfilter_zi(b: np.ndarray, a: np.ndarray) -> np.ndarray:
+    """Steady-state initial conditions of the step response (scipy.signal.lfilter_zi) for len(a) == len(b)."""
+    b, a = np.asarray(b, np.float64) / a[0], np.asarray(a, np.float64) / a[0]
+    n = len(a)
+    comp = np.zeros((n - 1, n - 1))
+    comp[0, :] = -a[1:]
+    comp[1:, :-1] = np.eye(n - 2)
+    i_minus_a = np.eye(n - 1) - comp.T
+    rhs = b[1:] - a[1:] * b[0]
+    return np.linalg.solve(i_minus_a, rhs)
+
+
+BANDPASS_PAD = 27
+
+
+def bandpass_coefficients(low_hz: float = 85.0, high_hz: float = 3400.0, sample_rate: int = SAMPLE_RATE) -> np.ndarray:
+    """[b (9) | a (9) | zi (8)] float64 for the reference's 4th-order Butterworth band-pass
+    (/root/reference/vocal_separation.py:351-357)."""
+    b, a = butter_bandpass(4, low_hz, high_hz, sample_rate)
+    return np.ascontiguousarray(np.concatenate([b, a, lfilter_zi(b, a)]))
+
+
+def bandpass_filter(audio_dev: torch.Tensor, offsets: np.ndarray, coeffs: np.ndarray) -> torch.Tensor:
+    """scipy.signal.filtfilt(b, a, chunk) for every chunk [offsets[i], offsets[i+1]) of a device buffer; returns a new
+    fp32 device tensor of the same layout.  Chunks of <= 27 samples come back unchanged."""
+    import ctypes as C
+    lib = _lib.load()
+    device = audio_dev.device
+    n = len(offsets) - 1
+    out = torch.empty_like(audio_dev)
+    if n <= 0:
+        return out
+    assert coeffs.dtype == np.float64 and coeffs.shape == (26,)
+    off_dev = torch.from_numpy(np.asarray(offsets, dtype=np.int64)).to(device, non_blocking=True)
+    scratch = torch.empty((n, BANDPASS_PAD), dtype=torch.float32, device=device)
+    _lib.check(lib.b200w_bandpass_filtfilt(audio_dev.data_ptr(), off_dev.data_ptr(), n,
+                                           coeffs.ctypes.data_as(C.POINTER(C.c_double)), out.data_ptr(),
+                                           scratch.data_ptr(), _stream_ptr(device)))
+    return out

@@ -162,3 +162,67 @@ class BatchedASR(B200WhisperASR):
 
     def __init__(self, lan, batcher: StreamBatcher, **kw):
         super().__init__(lan, model=_BatchedModel(batcher), **kw)
+
+
+class MultiGpuModel:
+    """ONE entry point for many streams on several GPUs of one box, in one process.
+
+    The reference picks a single GPU by free memory (/root/reference/一键实时识别麦克风.py:208-213).  Streams are
+    independent, so here they are sharded over the GPUs with no data-path collective: every GPU holds a full model
+    (replicated bf16 weights), a stream is pinned to a GPU by its key (sticky: ``shard_streams``), and a call's clips
+    are handed to their GPUs' worker threads concurrently (the C calls release the GIL; each engine has its own CUDA
+    streams and mutex, kernel attributes and SM counts are per device).  ``transcribe_batch`` has the signature of
+    ``B200WhisperModel.transcribe_batch`` -- so ``BatchedOnlineASR`` / ``StreamBatcher`` run on top of it unchanged --
+    plus ``keys=`` to name the streams (default: position in the call, which is sticky when callers keep their order).
+    One process per GPU under torchrun (bench.py) remains the other way to scale; results are identical either way."""
+
+    def __init__(self, model_factory, devices: Sequence[int]):
+        from concurrent.futures import ThreadPoolExecutor
+        self.devices = list(devices)
+        if not self.devices:
+            raise ValueError("MultiGpuModel needs at least one device")
+        self.models = [model_factory(d) for d in self.devices]
+        self.max_batch = sum(getattr(m, "max_batch", 8) for m in self.models)
+        self.dims = self.models[0].dims
+        self._pool = ThreadPoolExecutor(max_workers=len(self.devices), thread_name_prefix="b200w-gpu")
+        self.calls_per_device = [0] * len(self.devices)
+
+    def __getattr__(self, name):  # tokenizer(), alignment_heads, ... come from the first replica
+        return getattr(self.models[0], name)
+
+    def placement(self, keys: Sequence[Hashable]) -> List[int]:
+        """Replica index of every key: sorted keys dealt round-robin (the same rule as shard_streams)."""
+        shards = shard_streams(list(dict.fromkeys(keys)), len(self.models))
+        where = {k: r for r, ks in shards.items() for k in ks}
+        return [where[k] for k in keys]
+
+    def transcribe_batch(self, audios, languages=None, initial_prompts=None, keys: Optional[Sequence[Hashable]] = None,
+                         **kw):
+        n = len(audios)
+        keys = list(range(n)) if keys is None else list(keys)
+        languages = list(languages) if languages is not None else [None] * n
+        prompts = list(initial_prompts) if initial_prompts is not None else None
+        place = self.placement(keys)
+        parts: Dict[int, List[int]] = {}
+        for i, r in enumerate(place):
+            parts.setdefault(r, []).append(i)
+
+        def run(r: int, idx: List[int]):
+            self.calls_per_device[r] += 1
+            extra = {"initial_prompts": [prompts[i] for i in idx]} if prompts is not None else {}
+            return self.models[r].transcribe_batch([audios[i] for i in idx], languages=[languages[i] for i in idx],
+                                                   **extra, **kw)
+
+        futures = {r: self._pool.submit(run, r, idx) for r, idx in parts.items()}
+        out: List[Any] = [None] * n
+        for r, idx in parts.items():
+            for i, res in zip(idx, futures[r].result()):
+                out[i] = res
+        return out
+
+    def transcribe(self, audio, language=None, **kw):
+        segments, info = self.transcribe_batch([audio], languages=[language], **kw)[0]
+        return iter(segments), info
+
+    def close(self):
+        self._pool.shutdown(wait=True)

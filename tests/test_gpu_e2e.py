@@ -150,6 +150,37 @@ def test_concurrent_lanes_give_identical_results(model):
             e.close()
 
 
+def test_multi_gpu_model_one_process(model):
+    """MultiGpuModel: one process, one replica per GPU, streams sharded by key.  Needs >= 2 GPUs (gpurun --gpus 2);
+    results are identical to the single-GPU model, and both devices actually ran kernels (per-device kernel
+    attributes and SM counts: a second GPU in one process used to fail to launch)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from realtime_whisper_asr_b200.scheduler import MultiGpuModel
+    from realtime_whisper_asr_b200.streaming import BatchedOnlineASR
+    sd = W.synthetic_state_dict(model.dims, seed=0)
+    mg = MultiGpuModel(lambda d: B200WhisperModel("tiny", state_dict=sd, dims=model.dims, device_index=d, max_batch=4,
+                                                  max_beam=5), [0, 1])
+    auds = [speech_like(240 + i, s) for i, s in enumerate([30.0, 7.0, 3.0, 12.0, 45.0, 1.0, 22.0])]
+    kw = dict(beam_size=5, temperature=0.0, word_timestamps=True, condition_on_previous_text=True)
+    want = model.transcribe_batch(auds, languages=["en"] * len(auds), **kw)
+    got = mg.transcribe_batch(auds, languages=["en"] * len(auds), **kw)
+    for (sa, _), (sb, _) in zip(want, got):
+        assert [s.tokens for s in sa] == [s.tokens for s in sb]
+        assert [(w.start, w.end) for s in sa for w in s.words] == [(w.start, w.end) for s in sb for w in s.words]
+    assert all(c > 0 for c in mg.calls_per_device)
+    # the batched streaming policy runs on top of it unchanged
+    pol = BatchedOnlineASR(mg, transcribe_kwargs={"beam_size": 1})
+    for i in range(6):
+        pol.add_stream(i, "en")
+    for it in range(3):
+        for i in range(6):
+            pol.insert_audio_chunk(i, auds[0][(it * 6 + i) * 8000:(it * 6 + i + 2) * 8000])
+        out = pol.process_iter()
+        assert len(out) == 6
+    mg.close()
+
+
 def test_language_detection_and_info(model):
     segs, info = model.transcribe(speech_like(5, 4.0), language=None, beam_size=1, temperature=0.0)
     assert info.language in model.supported_languages and 0.0 < info.language_probability <= 1.0

@@ -82,3 +82,34 @@ def test_stream_batcher_batches_concurrent_calls():
     for i in range(8):
         assert results[i] == [("seg", 100 + i, f"p{i}")]  # each caller gets its own result
     assert sum(model.batches) == 8 and max(model.batches) > 1 and b.requests_run == 8
+
+
+def test_multi_gpu_model_shards_and_restores_order():
+    import numpy as np
+    """MultiGpuModel (one process, one replica per device): sticky placement, every clip reaches exactly one replica,
+    results come back in input order, prompts follow their clips.  (Fake replicas: no GPU needed.)"""
+    from realtime_whisper_asr_b200.scheduler import MultiGpuModel
+
+    class Fake:
+        max_batch = 4
+        dims = "dims"
+
+        def __init__(self, dev):
+            self.dev, self.seen = dev, []
+
+        def transcribe_batch(self, audios, languages=None, initial_prompts=None, **kw):
+            self.seen.append(len(audios))
+            ps = initial_prompts or [None] * len(audios)
+            return [([("seg", self.dev, float(a[0]), p, l)], ("info", kw.get("beam_size"))) for a, p, l in zip(audios, ps, languages)]
+
+    mg = MultiGpuModel(Fake, [0, 1, 2])
+    auds = [np.full(10, float(i), np.float32) for i in range(10)]
+    out = mg.transcribe_batch(auds, languages=["en"] * 10, initial_prompts=[f"p{i}" for i in range(10)], beam_size=5)
+    assert [o[0][0][2] for o in out] == [float(i) for i in range(10)]          # input order restored
+    assert [o[0][0][3] for o in out] == [f"p{i}" for i in range(10)]          # prompts travel with their clips
+    assert sorted(sum(m.seen) for m in mg.models) == [3, 3, 4] and mg.max_batch == 12
+    place = mg.placement(list(range(10)))
+    assert place == mg.placement(list(range(10))) and [o[0][0][1] for o in out] == place   # sticky, and used
+    keyed = mg.transcribe_batch(auds[:4], languages=["en"] * 4, keys=["b", "a", "d", "c"])
+    assert [o[0][0][1] for o in keyed] == mg.placement(["b", "a", "d", "c"])
+    mg.close()
