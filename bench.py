@@ -12,7 +12,7 @@ the "peaked" synthetic model emits ~100-token transcripts ending in EOT, like re
   e2e       RTFx through the public host API (numpy in, Python Segment/Word objects out):
             pinned H2D of every chunk and D2H of the results inside the timed region
   roofline  the kernel with the largest share of the step: the decode-step cross attention
-            (cross_attn_tc_kernel, HBM-bound: every live (stream, head) reads its K and V once per
+            (cross_attn_sp_kernel, HBM-bound: every live (stream, head) reads its K and V once per
             layer per step).  Decode steps are replayed as CUDA graphs; the engine records CUDA events
             around this kernel's launch in the middle decoder layer as nodes of that graph
             (b200w_step_probe_*), so it is timed INSIDE the timed region, every decode step;
@@ -628,7 +628,7 @@ def run_b200(args, rank, world, local):
         # the middle decoder layer, every decode step; the other layers launch the same kernel on the same shapes
         gbs = pr_bytes.value / 1e9 / (pr_ms.value / 1e3)
         k_ms_step = pr_ms.value * n_dec_layers / args.steps
-        roofline = {"bound": "hbm", "kernel": "cross_attn_tc_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "cross_attn_sp_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": gbs / hbm_peak, "traffic": traffic_of("cross_tc_traffic.json"), "peak_source": hbm_src,
                     "launches_timed": int(pr_n.value), "kernel_ms_per_step": k_ms_step,
                     "share_of_step": k_ms_step / step_ms,
@@ -640,7 +640,7 @@ def run_b200(args, rank, world, local):
                                           "kernel_ms_per_step": x["ms"]} if x and x["ms"] > 0 else None)}
     elif x and x["ms"] > 0:
         gbs = x["work"] / 1e9 / (x["ms"] / 1e3)
-        roofline = {"bound": "hbm", "kernel": "cross_attn_tc_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "cross_attn_sp_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": gbs / hbm_peak, "traffic": traffic_of("cross_tc_traffic.json"), "peak_source": hbm_src,
                     "launches_timed": x["launches"], "kernel_ms_per_step": x["ms"],
                     "share_of_step": x["ms"] / step_ms,

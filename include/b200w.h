@@ -116,7 +116,7 @@ int b200w_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev,
 int b200w_skinny_gemm(const void* X_dev, const void* W_dev, const float* bias_dev, void* out_dev, int M, int N,
                       int K, int64_t ldx, int64_t ldw, int64_t ldo, int flags, int splits, void* stream);
 
-/* Decode-step cross attention on tcgen05 (csrc/attention.cu, cross_attn_tc_kernel): groups of <= 8 consecutive
+/* Decode-step cross attention on tcgen05 (csrc/attention.cu, cross_attn_sp_kernel): groups of <= 8 consecutive
  * query rows of one stream share one pass over that stream's keys / values.
  *   cross_kv_dev  bf16 [n_streams][n_layers][k|v][n_heads][len][64]       q_dev  bf16 [rows][n_heads*64]
  *   stream_dev    int32 [rows] stream of each row       g_start_dev / g_count_dev  int32 [n_groups]

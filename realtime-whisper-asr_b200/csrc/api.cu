@@ -66,7 +66,6 @@ uint64_t b200w_launch_count(void) { return g_launch_count.load(); }
 
 int b200w_gemm_set_trace(void* dev_buf) {
   if (getenv("B200W_TRACE_DSTEP")) dstep_set_trace(dev_buf, atoi(getenv("B200W_TRACE_DSTEP")));
-  else if (getenv("B200W_TRACE_CROSS")) cross_tc_set_trace(dev_buf);
   else if (getenv("B200W_TRACE_SKINNY")) skinny_set_trace(dev_buf);
   else gemm_set_trace(dev_buf);
   return 0;

@@ -6,8 +6,8 @@
 //    (T = 1500, operands = column ranges of the fused QKV activation) and cross attention for passes
 //    with many query rows per stream (prompts, the alignment pass): Q = activation rows of a segment,
 //    K/V = the per-chunk cross K/V blocks.
-//  * cross_attn_tc_kernel: decode-step cross attention, HBM-bound: K/V of every live (stream, head)
-//    stream once through a TMA ring, tcgen05 for both products, softmax pipelined into the loads.
+//  * cross_attn_sp_kernel: decode-step cross attention, HBM-bound: K/V of every live (stream, head)
+//    stream once through a TMA ring, tcgen05 for both products, single-pass softmax.
 //  * cross_attn_kernel / cross_attn_split_kernel: CUDA-core cross attention; the first exports the
 //    probabilities of the alignment heads, the second is the fallback of the tensor-core kernel.
 //  * dec_attn_kernel: decoder self-attention over the token-granular paged KV cache: one CTA per
@@ -919,26 +919,20 @@ static void launch_cross_split(const CrossAttnParams& p, int n_groups, int n_hea
   B200W_CHECK_CUDA(cudaGetLastError());
 }
 
-// ---- tensor-core variant for decode steps (no probability export).
-// One persistent CTA per SM walks the (live group, head) work items.  Per item the head's K and V
-// ([1500][64] bf16 each, 384 KB together) stream ONCE through a 12-slot TMA ring, prefetched across
-// phases and across items, and the arithmetic runs on tcgen05:
-//   S^T[keys x 16] = K_tile[128 keys x 64] . Q^T        (12 tiles -> 192 TMEM columns, keys = lanes)
-//   softmax over keys: every thread owns one key row of each tile (96 scores in registers)
+// ---- tensor-core variant for decode steps (no probability export): cross_attn_sp_kernel.
+// Persistent CTAs (two per SM) walk the (live group, head) work items.  Per item the head's K and V ([1500][64]
+// bf16 each, 384 KB together) stream ONCE through a TMA ring, and the arithmetic runs on tcgen05:
+//   S^T[keys x 16] = K_tile[128 keys x 64] . Q^T        (keys = TMEM lanes: the softmax is spread over 128 threads)
 //   O[128 x 64]   += P[128 x 128 keys] . V_tile[128 keys x 64]   (rows >= 8 of P are don't-care: a
 //   row of A only feeds the same row of D, so the operand tile may overlap unrelated shared memory)
-// Warps 0-3: Q staging, softmax, output.  Warp 4: TMA producer.  Warp 5: MMA issuer.
+// Warps 0-3: probabilities and output.  Warp 4: TMA producer (lane 0) and Q staging (lanes 1-31).  Warp 5: MMA issuer.
 // Load balance and batch invariance: every item is ALWAYS cut into the same `pieces` key ranges (a divisor of
 // the tile count, chosen by the caller from the shapes alone), the units (item, piece) are numbered item-major
 // and dealt to the CTAs in contiguous runs.  A piece leaves an un-normalised partial result in global scratch
 // and the last piece of an item to finish (atomic counter, self-resetting) merges them in piece order, so an
 // item's arithmetic never depends on how many other items share the launch.  pieces = 1: items are computed whole.
-static constexpr int XT_RING = 5;    // 16 KB slots; two CTAs share an SM and cover each other's softmax phases
 static constexpr int XT_MAX_TILES = 12;  // keys <= 1536
-static constexpr int XT_P_BYTES = XT_MAX_TILES * 2 * 1024;
 static constexpr int XT_Q_BYTES = 2048;
-static constexpr int XT_N_BARS = 2 * XT_RING + 2 * XT_MAX_TILES + 4;
-static constexpr int XT_SMEM = XT_P_BYTES + 2 * XT_Q_BYTES + XT_RING * TILE_BYTES + XT_N_BARS * 8 + 256 + 16 + 1024;
 static constexpr int XT_MAX_PIECES = 6;
 static constexpr int XT_CTAS_PER_SM = 2;
 static constexpr int XT_PART_FLOATS = 8 * 64 + 16;  // O[8][64], m[8], l[8]
@@ -960,9 +954,8 @@ struct CrossTcParams {
   int pieces;      // key ranges per item (divides the tile count; 1 = whole items)
   float* partial;  // [item][XT_MAX_PIECES][XT_PART_FLOATS]
   int* counters;   // [item], zero between launches
-  long long* trace;  // development aid: [cta][unit < 6][8] clock64 stamps, or null
+  int* err;        // set to 1 when a score exceeds the kernel's exponent range (checked by the engine)
 };
-#define XT_TRACE(slot) do { if (p.trace && it < 6) p.trace[(blockIdx.x * 6 + it) * 8 + (slot)] = clock64(); } while (0)
 
 struct XtUnit {
   int item, t0, t1, piece, n_pieces, tail_idx;
@@ -983,80 +976,54 @@ __device__ __forceinline__ bool xt_unit(int u, int n_items, int n_tiles, XtUnit&
   return true;
 }
 
-// Softmax of one unit, spread over the two streaming phases so that it hides behind the loads
-// (thread = key row of every tile; NQ live query columns per tile):
-//   pass 1, while the K tiles stream in: as soon as tile j's scores are in TMEM, fold them into the
-//           running per-query maximum;
-//   pass 2, while the V tiles stream in: P_j = exp2((s - max) * c) as bf16 into tile j's K-major operand
-//           buffer (row = query, column = key), released to the MMA issuer tile by tile.
-// Rows of dead queries (q >= NQ) keep stale values: they only feed output rows nobody reads.
-template <int NQ>
-__device__ __forceinline__ void xt_pass1(int len, uint32_t tS, uint32_t bar_s0, uint32_t parity, int t0, int nt,
-                                         float (&mx)[8]) {
-  const int key0 = t0 * 128 + (int)threadIdx.x;
-#pragma unroll 1
-  for (int j = 0; j < nt; ++j) {
-    mbar_wait(bar_s0 + 8 * j, parity);
-    tc_fence_after();
-    uint32_t sc[8];
-    tmem_ld8(tS + 16 * j, sc);
-    tmem_ld_wait();
-    if (key0 + j * 128 < len) {
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) mx[q] = fmaxf(mx[q], __uint_as_float(sc[q]));
-    }
-  }
-}
-template <int NQ>
-__device__ __forceinline__ void xt_pass2(int len, float scale_log2e, uint32_t tS, uint8_t* sP, uint32_t bar_p0, int t0,
-                                         int nt, const float (&mxs)[8], float (&sum)[8]) {
-  const int tid = threadIdx.x;
-  const int key0 = t0 * 128 + tid;
-  const int kc = tid & 63, half = tid >> 6;
-  uint8_t* prow = sP + half * 1024 + (kc & 7) * 2;
-#pragma unroll 1
-  for (int j = 0; j < nt; ++j) {
-    uint32_t sc[8];
-    tmem_ld8(tS + 16 * j, sc);
-    tmem_ld_wait();
-    const bool valid = key0 + j * 128 < len;
-    uint8_t* pt = prow + j * 2048;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const float e = valid ? ex2_approx(fmaf(__uint_as_float(sc[q]), scale_log2e, -mxs[q])) : 0.f;
-      sum[q] += e;
-      *reinterpret_cast<bf16*>(pt + q * 128 + (((kc >> 3) ^ q) << 4)) = __float2bfloat16(e);
-    }
-    fence_proxy_async_smem();
-    mbar_arrive(bar_p0 + 8 * j);
-  }
-}
+// ---- the kernel.  Single pass over the keys: a classic softmax needs the row maximum before the first probability
+// can be formed, i.e. all scores of a unit before any P.V product (round 1's kernel did that in two passes over the
+// TMEM-resident scores and kept 12 score tiles alive).  Here the reference value of the exponentials is the maximum
+// of the unit's FIRST tile: P = exp2(s c - m_0) is exact arithmetic for any reference
+// (bf16 / fp32 keep their relative precision over 2^+-126), and a later score exceeding m_0 by more than 2^100
+// -- which no attention row does -- raises an error flag that the engine turns into an exception (never silent).
+// Every tile then flows  K_j -> S_j = K_j Q^T -> P_j -> O += P_j V_j  with no unit-wide synchronisation:
+//   * K and V tiles interleaved in one TMA ring (K runs XS_LA tiles ahead of V), 6 slots;
+//   * 8 score slots in TMEM and 4 probability slots in shared memory, recycled through mbarriers;
+//   * O double-buffered in TMEM, so the output of unit i is read while unit i+1 accumulates.
+static constexpr int XS_RING = 6;
+static constexpr int XS_NS = 8;   // score slots (16 TMEM columns each)
+static constexpr int XS_NP = 4;   // probability slots (2 KB each)
+static constexpr int XS_LA = 2;   // the QK product runs this many tiles ahead of the PV product
+static constexpr int XS_P_BYTES = XS_NP * 2048;
+static constexpr int XS_N_BARS = 2 * XS_RING + 2 * XS_NS + 2 * XS_NP + 8;
+static constexpr int XS_SMEM = XS_P_BYTES + 2 * XT_Q_BYTES + XS_RING * TILE_BYTES + XS_N_BARS * 8 + 512 + 16 + 1024;
 
 __global__ void __launch_bounds__(192, 2)
-cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcParams p) {
+cross_attn_sp_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sP = smem;
-  uint8_t* sQ = sP + XT_P_BYTES;            // two [16][64] Q tiles (double-buffered across units)
+  uint8_t* sP = smem;                        // XS_NP slots of 2 KB (two 64-key halves of [8 queries][64] bf16)
+  uint8_t* sQ = sP + XS_P_BYTES;             // two [16][64] Q tiles (double-buffered across units)
   uint8_t* ring = sQ + 2 * XT_Q_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + XT_RING * TILE_BYTES);
-  float* s_red = reinterpret_cast<float*>(bars + XT_N_BARS);  // [2][4][8]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_red + 64);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + XS_RING * TILE_BYTES);
+  float* s_red = reinterpret_cast<float*>(bars + XS_N_BARS);  // [3][4][8]: tile-0 max, sums, running max
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_red + 96 + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * XT_RING;
-  const uint32_t bar_s0 = empty0 + 8 * XT_RING;           // [12] scores of tile j are in TMEM
-  const uint32_t bar_p0 = bar_s0 + 8 * XT_MAX_TILES;      // [12] P of tile j is in shared memory
-  const uint32_t bar_q0 = bar_p0 + 8 * XT_MAX_TILES;      // [2]  Q buffer b is staged
-  const uint32_t bar_sfree = bar_q0 + 16, bar_o = bar_sfree + 8;
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * XS_RING;
+  const uint32_t bar_s0 = empty0 + 8 * XS_RING;        // [NS] scores of the slot are in TMEM
+  const uint32_t bar_sf0 = bar_s0 + 8 * XS_NS;         // [NS] the softmax has read the slot
+  const uint32_t bar_p0 = bar_sf0 + 8 * XS_NS;         // [NP] probabilities of the slot are in shared memory
+  const uint32_t bar_pf0 = bar_p0 + 8 * XS_NP;         // [NP] the PV product has consumed the slot
+  const uint32_t bar_q0 = bar_pf0 + 8 * XS_NP;         // [2] Q buffer is staged
+  const uint32_t bar_qf0 = bar_q0 + 16;                // [2] the unit's QK products are done with the Q buffer
+  const uint32_t bar_o0 = bar_qf0 + 16;                // [2] O buffer is complete
+  const uint32_t bar_of0 = bar_o0 + 16;                // [2] O buffer has been read out
   pdl_trigger();
   if (tid == 0) {
-    for (int i = 0; i < 2 * XT_RING + XT_MAX_TILES; ++i) mbar_init(full0 + 8 * i, 1);   // ring + bar_s
-    for (int i = 0; i < XT_MAX_TILES; ++i) mbar_init(bar_p0 + 8 * i, 128);
+    for (int i = 0; i < 2 * XS_RING + XS_NS; ++i) mbar_init(full0 + 8 * i, 1);  // ring + bar_s
+    for (int i = 0; i < XS_NS; ++i) mbar_init(bar_sf0 + 8 * i, 128);
+    for (int i = 0; i < XS_NP; ++i) mbar_init(bar_p0 + 8 * i, 128);
+    for (int i = 0; i < XS_NP; ++i) mbar_init(bar_pf0 + 8 * i, 1);
     mbar_init(bar_q0, 31);
     mbar_init(bar_q0 + 8, 31);
-    mbar_init(bar_sfree, 128);
-    mbar_init(bar_o, 1);
+    for (int i = 0; i < 6; ++i) mbar_init(bar_qf0 + 8 * i, 1);  // qfree[2], o[2], ofree[2]
     fence_barrier_init();
     tma_prefetch_desc(&tmKV);
   }
@@ -1067,27 +1034,29 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_S = *tmem_slot, tmem_O = tmem_S + 16 * XT_MAX_TILES;
+  const uint32_t tmem_S = *tmem_slot, tmem_O = tmem_S + 16 * XS_NS;  // S slots [0,128), O buffers at 128 and 192
   const int n_tiles = (p.len + 127) >> 7;
-  // K/V and the pass metadata were written long before the kernel ahead of this one started, so the
-  // producer may run ahead of the dependency wait; Q (read) and the output (written) may not.
   const int n_items = *p.n_live_groups * p.n_heads;
   XtUnit un;
 
   if (warp == 4) {
-    if (lane == 0) {  // ---------------- TMA producer: K tiles then V tiles of every unit
+    if (lane == 0) {  // ---------------- TMA producer: K_j and V_(j-LA) interleaved, in the order the MMA warp consumes them
       uint32_t slot = 0, phase = 0;
       for (int u = 0; xt_unit(u, n_items, n_tiles, un, p.pieces); ++u) {
         const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
         const int blk = p.stream[p.g_start[g]] * p.blocks_per_stream + p.layer_block0 + h;
-        for (int kv = 0; kv < 2; ++kv)
-          for (int j = un.t0; j < un.t1; ++j) {
+        const int nt = un.t1 - un.t0;
+        for (int j = 0; j < nt + XS_LA; ++j) {
+          for (int kv = 0; kv < 2; ++kv) {
+            const int tile = kv == 0 ? j : j - XS_LA;
+            if (tile < 0 || tile >= nt) continue;
             mbar_wait(empty0 + 8 * slot, phase ^ 1);
             const uint32_t fb = full0 + 8 * slot;
             mbar_arrive_expect_tx(fb, TILE_BYTES);
-            tma_load_3d(smem_u32(ring + slot * TILE_BYTES), &tmKV, fb, 0, j * 128, blk + kv * p.n_heads);
-            if (++slot == XT_RING) { slot = 0; phase ^= 1; }
+            tma_load_3d(smem_u32(ring + slot * TILE_BYTES), &tmKV, fb, 0, (un.t0 + tile) * 128, blk + kv * p.n_heads);
+            if (++slot == XS_RING) { slot = 0; phase ^= 1; }
           }
+        }
       }
     } else {  // ---------------- lanes 1..31: stage the Q tile of unit `it` one unit ahead of its use
       pdl_wait();
@@ -1103,8 +1072,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
           if (i < 128 && qr < nq)
             u[r] = *reinterpret_cast<const uint4*>(p.q + (long long)(q0 + qr) * p.q_stride + h * HD + 8 * ch);
         }
-        // buffer it&1 was last read by the QK MMAs of unit it-2: its last score barrier tells when they are done
-        if (it >= 2) mbar_wait(bar_s0 + 8 * (n_tiles / p.pieces - 1), (uint32_t)(it & 1));  // every unit has the same tile count
+        // buffer it&1 was last read by the QK products of unit it-2
+        mbar_wait(bar_qf0 + 8 * (it & 1), (uint32_t)(((it >> 1) & 1) ^ 1));
         uint8_t* dst = sQ + (it & 1) * XT_Q_BYTES;
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
@@ -1120,102 +1089,157 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
     if (lane == 0) {  // ---------------- MMA issuer
       constexpr uint32_t idescS = make_idesc_bf16(128, 16, 0, 0);  // K (K-major) x Q (K-major)
       constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);  // P (K-major) x V (MN-major)
-      uint32_t slot = 0, phase = 0;
+      uint32_t slot = 0, phase = 0, g0 = 0;
       for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.pieces); ++it) {
         const int nt = un.t1 - un.t0;
-        const uint32_t par = it & 1;
-        mbar_wait(bar_q0 + 8 * par, (uint32_t)((it >> 1) & 1));
-        if (it > 0) mbar_wait(bar_sfree, par ^ 1);  // the softmax of the unit before is done with the scores
+        const uint32_t par = it & 1, upar = (uint32_t)((it >> 1) & 1);
+        mbar_wait(bar_q0 + 8 * par, upar);
         tc_fence_after();
         const uint64_t qd = make_sw128_desc(smem_u32(sQ + par * XT_Q_BYTES));
-        for (int j = 0; j < nt; ++j) {
-          mbar_wait(full0 + 8 * slot, phase);
-          tc_fence_after();
-          const uint64_t kd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
+        const uint32_t d_o = tmem_O + 64 * par;
+        for (int j = 0; j < nt + XS_LA; ++j) {
+          if (j < nt) {  // S_j = K_j Q^T
+            const uint32_t gs = g0 + j, ss = gs % XS_NS, us = gs / XS_NS;
+            mbar_wait(full0 + 8 * slot, phase);
+            mbar_wait(bar_sf0 + 8 * ss, (us & 1u) ^ 1u);
+            tc_fence_after();
+            const uint64_t kd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_S + 16 * j, kd + 2 * k, qd + 2 * k, idescS, k != 0);
-          tc_commit(empty0 + 8 * slot);
-          tc_commit(bar_s0 + 8 * j);
-          if (++slot == XT_RING) { slot = 0; phase ^= 1; }
-        }
-        for (int j = 0; j < nt; ++j) {
-          mbar_wait(bar_p0 + 8 * j, par);
-          mbar_wait(full0 + 8 * slot, phase);
-          tc_fence_after();
-          const uint64_t vd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t pd = make_sw128_desc(smem_u32(sP + (j * 2 + (k >> 2)) * 1024)) + 2 * (k & 3);
-            tc_mma_bf16(tmem_O, pd, vd + 128 * k, idescO, (j | k) != 0);
+            for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_S + 16 * ss, kd + 2 * k, qd + 2 * k, idescS, k != 0);
+            tc_commit(empty0 + 8 * slot);
+            tc_commit(bar_s0 + 8 * ss);
+            if (j == nt - 1) tc_commit(bar_qf0 + 8 * par);
+            if (++slot == XS_RING) { slot = 0; phase ^= 1; }
           }
-          tc_commit(empty0 + 8 * slot);
-          if (++slot == XT_RING) { slot = 0; phase ^= 1; }
+          if (j >= XS_LA) {  // O += P_jj V_jj
+            const int jj = j - XS_LA;
+            const uint32_t gp = g0 + jj, ps = gp % XS_NP, up = gp / XS_NP;
+            if (jj == 0) mbar_wait(bar_of0 + 8 * par, upar ^ 1u);  // the output of unit it-2 has left this O buffer
+            mbar_wait(bar_p0 + 8 * ps, up & 1u);
+            mbar_wait(full0 + 8 * slot, phase);
+            tc_fence_after();
+            const uint64_t vd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t pd = make_sw128_desc(smem_u32(sP + (ps * 2 + (k >> 2)) * 1024)) + 2 * (k & 3);
+              tc_mma_bf16(d_o, pd, vd + 128 * k, idescO, (jj | k) != 0);
+            }
+            tc_commit(empty0 + 8 * slot);
+            tc_commit(bar_pf0 + 8 * ps);
+            if (++slot == XS_RING) { slot = 0; phase ^= 1; }
+          }
         }
-        tc_commit(bar_o);
+        tc_commit(bar_o0 + 8 * par);
+        g0 += nt;
       }
     }
-  } else {  // ---------------- warps 0..3: softmax (thread = key row of every tile) and output
+  } else {  // ---------------- warps 0..3: probabilities (thread = key row of every tile) and output
     pdl_wait();
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    const int kc = tid & 63, half = tid >> 6;
+    uint32_t g0 = 0;
     for (int it = 0; xt_unit(it, n_items, n_tiles, un, p.pieces); ++it) {
       const int g = un.item / p.n_heads, h = un.item - g * p.n_heads;
       const int q0 = p.g_start[g], nq = p.g_count[g];
       const int nt = un.t1 - un.t0;
-      const uint32_t par = it & 1;
-      if (tid == 0) XT_TRACE(0);
-      float mx[8], sum[8];
+      const uint32_t par = it & 1, upar = (uint32_t)((it >> 1) & 1);
+      const int key0 = un.t0 * 128 + tid;
+      float mref[8], sum[8], gmx[8];
+      uint32_t sc[8];
+      // reference value: the maximum of the unit's first tile
+      {
+        const uint32_t ss = g0 % XS_NS, us = g0 / XS_NS;
+        mbar_wait(bar_s0 + 8 * ss, us & 1u);
+        tc_fence_after();
+        tmem_ld8(tmem_S + lane_sel + 16 * ss, sc);
+        tmem_ld_wait();
+        const bool valid = key0 < p.len;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { mx[q] = -INFINITY; sum[q] = 0.f; }
-      if (nq <= 1) xt_pass1<1>(p.len, tmem_S + lane_sel, bar_s0, par, un.t0, nt, mx);
-      else if (nq <= 2) xt_pass1<2>(p.len, tmem_S + lane_sel, bar_s0, par, un.t0, nt, mx);
-      else if (nq <= 5) xt_pass1<5>(p.len, tmem_S + lane_sel, bar_s0, par, un.t0, nt, mx);
-      else xt_pass1<8>(p.len, tmem_S + lane_sel, bar_s0, par, un.t0, nt, mx);
-      if (tid == 0) XT_TRACE(1);
+        for (int q = 0; q < 8; ++q) {
+          float v = valid ? __uint_as_float(sc[q]) : -INFINITY;
+          for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+          mref[q] = v;
+        }
+        if (lane < 8) {
+          float v = mref[0];
+#pragma unroll
+          for (int q = 1; q < 8; ++q) v = lane == q ? mref[q] : v;
+          s_red[warp * 8 + lane] = v;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          mref[q] = fmaxf(fmaxf(s_red[q], s_red[8 + q]), fmaxf(s_red[16 + q], s_red[24 + q])) * p.scale_log2e;
+          sum[q] = 0.f;
+          gmx[q] = -INFINITY;
+        }
+      }
+#pragma unroll 1
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t gs = g0 + j, ss = gs % XS_NS, us = gs / XS_NS, ps = gs % XS_NP, up = gs / XS_NP;
+        if (j > 0) {
+          mbar_wait(bar_s0 + 8 * ss, us & 1u);
+          tc_fence_after();
+          tmem_ld8(tmem_S + lane_sel + 16 * ss, sc);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(bar_sf0 + 8 * ss);  // the slot may take the scores of tile j + NS
+        mbar_wait(bar_pf0 + 8 * ps, (up & 1u) ^ 1u);  // the PV product of tile j - NP is done with this slot
+        const bool valid = key0 + j * 128 < p.len;
+        uint8_t* pt = sP + ps * 2048 + half * 1024 + (kc & 7) * 2;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q < nq) {
+            const float sv = __uint_as_float(sc[q]);
+            const float e = valid ? ex2_approx(fmaf(sv, p.scale_log2e, -mref[q])) : 0.f;
+            sum[q] += e;
+            gmx[q] = valid ? fmaxf(gmx[q], sv) : gmx[q];
+            *reinterpret_cast<bf16*>(pt + q * 128 + (((kc >> 3) ^ q) << 4)) = __float2bfloat16(e);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_p0 + 8 * ps);
+      }
+      g0 += nt;
+      // unit end: row sums and the overflow guard
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        for (int o = 16; o > 0; o >>= 1) mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
+        for (int o = 16; o > 0; o >>= 1) {
+          sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
+          gmx[q] = fmaxf(gmx[q], __shfl_xor_sync(0xffffffffu, gmx[q], o));
+        }
       }
       if (lane < 8) {
-        float v = mx[0];
+        float v = sum[0], m = gmx[0];
 #pragma unroll
-        for (int q = 1; q < 8; ++q) v = lane == q ? mx[q] : v;
-        s_red[warp * 8 + lane] = v;
+        for (int q = 1; q < 8; ++q) { v = lane == q ? sum[q] : v; m = lane == q ? gmx[q] : m; }
+        s_red[32 + warp * 8 + lane] = v;
+        s_red[64 + warp * 8 + lane] = m;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        mx[q] = fmaxf(fmaxf(s_red[q], s_red[8 + q]), fmaxf(s_red[16 + q], s_red[24 + q])) * p.scale_log2e;
-      if (nq <= 1) xt_pass2<1>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, bar_p0, un.t0, nt, mx, sum);
-      else if (nq <= 2) xt_pass2<2>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, bar_p0, un.t0, nt, mx, sum);
-      else if (nq <= 5) xt_pass2<5>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, bar_p0, un.t0, nt, mx, sum);
-      else xt_pass2<8>(p.len, p.scale_log2e, tmem_S + lane_sel, sP, bar_p0, un.t0, nt, mx, sum);
-      tc_fence_before();
-      mbar_arrive(bar_sfree);  // scores consumed: the next unit's QK MMAs may overwrite them
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        for (int o = 16; o > 0; o >>= 1) sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
-      }
-      if (lane < 8) {
-        float v = sum[0];
-#pragma unroll
-        for (int q = 1; q < 8; ++q) v = lane == q ? sum[q] : v;
-        s_red[32 + warp * 8 + lane] = v;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // partial sums visible to warp 0
-      if (tid == 0) XT_TRACE(2);
-      mbar_wait(bar_o, par);
-      tc_fence_after();
-      if (tid == 0) XT_TRACE(3);
       if (warp == 0) {
-        // the other warps' partial sums were stored before their arrive on bar_p, which bar_o follows
-        const float lsum = lane < 8 ? s_red[32 + lane] + s_red[40 + lane] + s_red[48 + lane] + s_red[56 + lane] : 1.f;
+        mbar_wait(bar_o0 + 8 * par, upar);
+        tc_fence_after();
+        float lsum = 1.f, mr = 0.f;
+        if (lane < 8) {
+          lsum = s_red[32 + lane] + s_red[40 + lane] + s_red[48 + lane] + s_red[56 + lane];
+          const float gm = fmaxf(fmaxf(s_red[64 + lane], s_red[72 + lane]), fmaxf(s_red[80 + lane], s_red[88 + lane]));
+          mr = fmaxf(fmaxf(s_red[lane], s_red[8 + lane]), fmaxf(s_red[16 + lane], s_red[24 + lane])) * p.scale_log2e;
+          if (lane < nq && gm * p.scale_log2e - mr > 100.f) atomicExch(p.err, 1);  // never silent
+        }
         float* rec = p.partial + ((long long)un.tail_idx * XT_MAX_PIECES + un.piece) * XT_PART_FLOATS;
         const float inv = 1.0f / lsum;
-#pragma unroll 1
-        for (int hc = 0; hc < 2; ++hc) {  // 32 output dims at a time (lane = query row)
-          uint32_t o[32];
-          tmem_ld32(tmem_O + 32 * hc, o);
-          tmem_ld_wait();
+        uint32_t o_lo[32], o_hi[32];
+        tmem_ld32(tmem_O + 64 * par, o_lo);
+        tmem_ld32(tmem_O + 64 * par + 32, o_hi);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_of0 + 8 * par);  // the buffer may take unit it + 2
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {
+          const uint32_t* o = hc == 0 ? o_lo : o_hi;
           if (un.n_pieces == 1) {
             if (lane < nq) {
               bf16* dst = p.out + (long long)(q0 + lane) * p.out_stride + h * HD + 32 * hc;
@@ -1230,7 +1254,6 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
               }
             }
           } else if (lane < 8) {
-            // piece of a split item: un-normalised partial result -> scratch; the last piece merges
             float4* dst = reinterpret_cast<float4*>(rec + lane * 64 + 32 * hc);
 #pragma unroll
             for (int c = 0; c < 32; c += 4)
@@ -1240,8 +1263,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
         }
         if (un.n_pieces > 1) {
           if (lane < 8) {
-            rec[512 + lane] = fmaxf(fmaxf(s_red[lane], s_red[8 + lane]), fmaxf(s_red[16 + lane], s_red[24 + lane])) *
-                              p.scale_log2e;
+            rec[512 + lane] = mr;
             rec[520 + lane] = lsum;
           }
           __threadfence();
@@ -1255,13 +1277,13 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
             const int q = lane >> 2, c0 = (lane & 3) * 16;  // lane -> (query, 16 dims)
             float M = -INFINITY;
             for (int s2 = 0; s2 < un.n_pieces; ++s2) M = fmaxf(M, __ldcg(base + s2 * XT_PART_FLOATS + 512 + q));
-            float L = 0.f, acc[16];
+            float Lsum = 0.f, acc[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = 0.f;
             for (int s2 = 0; s2 < un.n_pieces; ++s2) {
               const float* r2 = base + s2 * XT_PART_FLOATS;
               const float w = ex2_approx(__ldcg(r2 + 512 + q) - M);
-              L = fmaf(__ldcg(r2 + 520 + q), w, L);
+              Lsum = fmaf(__ldcg(r2 + 520 + q), w, Lsum);
 #pragma unroll
               for (int i = 0; i < 16; i += 4) {
                 const float4 v = __ldcg(reinterpret_cast<const float4*>(r2 + q * 64 + c0 + i));
@@ -1270,7 +1292,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
               }
             }
             if (q < nq) {
-              const float invL = 1.0f / L;
+              const float invL = 1.0f / Lsum;
               bf16* dst = p.out + (long long)(q0 + q) * p.out_stride + h * HD + c0;
               uint4 u, w4;
               __nv_bfloat162* u2 = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -1287,10 +1309,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
           }
         }
       }
-      tc_fence_before();
-      // s_red / sP are rewritten by the next unit: everyone must be past their reads first
+      // s_red is rewritten by the next unit: everyone must be past their reads first
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tid == 0) XT_TRACE(4);
     }
   }
   tc_fence_before();
@@ -1301,13 +1321,12 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
   }
 }
 
-static long long* g_xt_trace = nullptr;
-void cross_tc_set_trace(void* dev_buf) { g_xt_trace = static_cast<long long*>(dev_buf); }
 
 static constexpr int XT_MAX_ITEMS = 64 * 32;  // (live group, head) items per launch: <= 64 groups, <= 32 heads
 size_t cross_attention_tc_scratch_bytes() {
-  return (size_t)XT_MAX_ITEMS * (XT_MAX_PIECES * XT_PART_FLOATS * sizeof(float) + sizeof(int)) + 256;
+  return (size_t)XT_MAX_ITEMS * (XT_MAX_PIECES * XT_PART_FLOATS * sizeof(float) + sizeof(int)) + 1024;
 }
+size_t cross_attention_tc_error_offset() { return (size_t)XT_MAX_ITEMS * sizeof(int); }
 
 void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int layer, int n_heads, int len,
                         const bf16* q, int q_stride, const int* stream, const int* g_start, const int* g_count,
@@ -1318,7 +1337,6 @@ void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int l
   CUtensorMap tm;
   make_tmap_bf16_3d(&tm, cross_kv, HD, len, (uint64_t)n_streams * n_layers * 2 * n_heads, HD, (uint64_t)len * HD, HD,
                     128);
-  ensure_dynamic_smem(cross_attn_tc_kernel, XT_SMEM);
   CrossTcParams p;
   p.q = q; p.q_stride = q_stride; p.stream = stream; p.g_start = g_start; p.g_count = g_count;
   p.n_live_groups = n_live_groups; p.n_heads = n_heads; p.blocks_per_stream = n_layers * 2 * n_heads;
@@ -1330,11 +1348,12 @@ void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int l
   B200W_REQUIRE(n_groups * n_heads <= XT_MAX_ITEMS, "cross_attention_tc: too many (group, head) items");
   // scratch: zero-initialised once by the owner; [XT_MAX_ITEMS counters][XT_MAX_ITEMS * pieces * record]
   p.counters = static_cast<int*>(scratch);
-  p.partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + ((XT_MAX_ITEMS * sizeof(int) + 255) & ~(size_t)255));
-  p.trace = g_xt_trace;
+  p.err = p.counters + XT_MAX_ITEMS;
+  p.partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + (((XT_MAX_ITEMS + 64) * sizeof(int) + 255) & ~(size_t)255));
   const int units = n_groups * n_heads * pieces;
   const int max_ctas = XT_CTAS_PER_SM * num_sms();
-  launch_pdl(cross_attn_tc_kernel, dim3(units < max_ctas ? units : max_ctas), dim3(192), (size_t)XT_SMEM, cs, tm, p);
+  ensure_dynamic_smem(cross_attn_sp_kernel, XS_SMEM);
+  launch_pdl(cross_attn_sp_kernel, dim3(units < max_ctas ? units : max_ctas), dim3(192), (size_t)XS_SMEM, cs, tm, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }

@@ -97,13 +97,14 @@ void cross_attention_flash(const bf16* cross_kv, int n_streams, int n_layers, in
 // Decode-step cross attention on tcgen05 (no probability export).  cross_kv is the whole per-chunk
 // buffer [n_streams][n_layers][k|v][n_heads][len][64]; groups [0, *n_live_groups) are processed, each
 // with g_count <= 8 live rows starting at g_start.
-void cross_tc_set_trace(void* dev_buf);  // development aid: per-item phase timestamps
 // pieces: every (group, head) item is cut into this many key ranges (must divide the tile count ceil(len/128),
 // else 1), computed by different CTAs and merged in piece order: a function of the shapes only, never of how many
 // items share the launch, so a stream's result does not depend on what is batched next to it.
 // scratch: cross_attention_tc_scratch_bytes() bytes, zeroed once (partial results of the pieces and their
 // self-resetting arrival counters).
 size_t cross_attention_tc_scratch_bytes();
+// byte offset (inside the scratch) of the int the kernel sets when a score leaves its exponent range
+size_t cross_attention_tc_error_offset();
 void cross_attention_tc(const bf16* cross_kv, int n_streams, int n_layers, int layer, int n_heads, int len,
                         const bf16* q, int q_stride, const int* stream, const int* g_start, const int* g_count,
                         const int* n_live_groups, int n_groups, bf16* out, int out_stride, float scale, void* scratch,

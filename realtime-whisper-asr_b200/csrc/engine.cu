@@ -1304,6 +1304,16 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     }
     t_book += ms_since(t_s2);
   }
+  {  // the single-pass cross attention raises a flag instead of returning numbers it cannot represent
+    int flag = 0;
+    char* fp = e->x_tc.as<char>() + cross_attention_tc_error_offset();
+    B200W_CHECK_CUDA(cudaMemcpyAsync(&flag, fp, 4, cudaMemcpyDeviceToHost, s));
+    B200W_CHECK_CUDA(cudaStreamSynchronize(s));
+    if (flag) {
+      B200W_CHECK_CUDA(cudaMemsetAsync(fp, 0, 4, s));
+      throw Error("cross attention: a score exceeds the first key tile's maximum by more than 2^100");
+    }
+  }
   e->optimer.collect("decode (prefill + steps)");
   if (timing)
     fprintf(stderr, "[b200w_decode] B=%d K=%d steps=%d prefill+first=%.2f ms, per step: fill %.3f ms, launch+gpu %.3f ms, "
