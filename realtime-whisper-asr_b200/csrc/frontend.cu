@@ -11,6 +11,7 @@
 // /root/reference/audio_deduplicator.py:60-181.
 #include <math.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.h"
@@ -656,10 +657,14 @@ static void build_tables(MelTables& t, int n_mels) {
 }
 
 static const MelTables* device_tables(int n_mels) {
-  static MelTables* d80 = nullptr;
-  static MelTables* d128 = nullptr;
-  MelTables** slot = n_mels == 80 ? &d80 : &d128;
+  // one copy per (device, n_mels): a table uploaded to GPU 0 is not addressable from GPU 1's kernels
+  static MelTables* tabs[64][2] = {};
+  static std::mutex mu;
   B200W_REQUIRE(n_mels == 80 || n_mels == 128, "n_mels must be 80 or 128");
+  int dev = 0;
+  B200W_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  MelTables** slot = &tabs[dev & 63][n_mels == 80 ? 0 : 1];
   if (!*slot) {
     MelTables* h = new MelTables();
     build_tables(*h, n_mels);
