@@ -101,6 +101,20 @@ int b200w_dedup_features(const float* audio_dev, const int64_t* offsets_dev, int
 int b200w_bandpass_filtfilt(const float* audio_dev, const int64_t* offsets_dev, int n_chunks,
                             const double* coeffs_host, float* out_dev, float* scratch_dev, void* stream);
 
+/* Batched VAD gate: the reference's DynamicVADIterator (/root/reference/asr_components.py:12-78 = upstream
+ * FixedVADIterator re-chunking + VADIterator state machine with a live-tunable min_silence_samples) for many streams.
+ *   b200w_vad_window_energy  built-in scorer: probs[w] = rms / (rms + k) of window w (fp32 [n_windows][512]); any
+ *                            other scorer (a batched Silero network) fills the same probs buffer instead
+ *   b200w_vad_gate           one thread per stream: windows [win_offsets[s], win_offsets[s+1]) in order through the
+ *                            state machine; state int64 [n_streams][3] = (triggered, temp_end, current_sample) is
+ *                            updated in place; min_silence_dev double [n_streams] (samples); events int64
+ *                            [n_streams][4] = (has_start, start, has_end, end) merged over the call's windows as
+ *                            FixedVADIterator.__call__ merges them */
+int b200w_vad_window_energy(const float* windows_dev, int n_windows, float k, float* probs_dev, void* stream);
+int b200w_vad_gate(const float* probs_dev, const int32_t* win_offsets_dev, int n_streams, int64_t* state_dev,
+                   const double* min_silence_dev, float threshold, int64_t speech_pad_samples, int64_t* events_dev,
+                   void* stream);
+
 /* ---------------------------------------------------------------- building blocks (tests) ---- */
 
 /* out[M][N] = act(A[M][K] * W[N][K]^T + bias) + residual.  bf16 operands, fp32 accumulate on

@@ -55,6 +55,8 @@ SIGNATURES = {
     "b200w_pack_windows": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "b200w_dedup_features": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "b200w_bandpass_filtfilt": (_i, [_vp, _vp, _i, C.POINTER(C.c_double), _vp, _vp, _vp]),
+    "b200w_vad_window_energy": (_i, [_vp, _i, _f, _vp, _vp]),
+    "b200w_vad_gate": (_i, [_vp, _vp, _i, _vp, _vp, _f, _i64, _vp, _vp]),
     "b200w_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _vp]),
     "b200w_skinny_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _vp]),
     "b200w_cross_attention_tc_scratch_bytes": (C.c_int64, []),

@@ -138,6 +138,22 @@ int b200w_bandpass_filtfilt(const float* audio_dev, const int64_t* offsets_dev, 
   B200W_API_END
 }
 
+int b200w_vad_window_energy(const float* windows_dev, int n_windows, float k, float* probs_dev, void* stream) {
+  B200W_API_BEGIN
+  vad_window_energy_launch(windows_dev, n_windows, k, probs_dev, static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+int b200w_vad_gate(const float* probs_dev, const int32_t* win_offsets_dev, int n_streams, int64_t* state_dev,
+                   const double* min_silence_dev, float threshold, int64_t speech_pad_samples, int64_t* events_dev,
+                   void* stream) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(probs_dev && win_offsets_dev && state_dev && min_silence_dev && events_dev, "null argument");
+  vad_gate_launch(probs_dev, win_offsets_dev, n_streams, reinterpret_cast<long long*>(state_dev), min_silence_dev,
+                  threshold, (long long)speech_pad_samples, reinterpret_cast<long long*>(events_dev),
+                  static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
 int b200w_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev,
                     const void* residual_dev, void* out_dev, int M, int N, int K, int64_t lda,
                     int64_t ldw, int64_t ldr, int64_t ldo, int flags, int force_bn, void* stream) {

@@ -863,4 +863,92 @@ void bandpass_filtfilt_launch(const float* audio, const long long* offsets, int 
   B200W_CHECK_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------- batched VAD gate
+// The reference gates every stream through DynamicVADIterator (/root/reference/asr_components.py:12-78): incoming
+// audio is re-chunked to 512-sample windows, a speech probability p is computed per window (Silero on the CPU), and
+// upstream's VADIterator state machine turns the p sequence into {start} / {end} events (start when p >= threshold
+// and not triggered; end when p < threshold - 0.15 for at least min_silence_samples).  For hundreds of
+// streams: one launch scores all windows of all streams, a second one runs every stream's state machine (one thread
+// per stream, windows in order) and merges the events of a call exactly as FixedVADIterator.__call__ does.
+// vad_window_energy_kernel is the built-in scorer p = rms / (rms + k) (the energy stand-in the tests use for the
+// un-vendored Silero network); any other scorer just writes the same probs buffer.
+__global__ void vad_window_energy_kernel(const float* __restrict__ windows, int n_windows, float k,
+                                         float* __restrict__ probs) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= n_windows) return;
+  const float4* src = reinterpret_cast<const float4*>(windows + (long long)w * 512);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // 128 float4 per window, coalesced
+    const float4 v = src[lane + 32 * i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const float rms = sqrtf(acc / 512.0f);
+    probs[w] = rms / (rms + k);
+  }
+}
+
+// state per stream: [triggered, temp_end, current_sample] (int64), min_silence_samples (double: the reference stores
+// sampling_rate * ms / 1000 as a float).  events per stream per call: [has_start, start, has_end, end].
+__global__ void vad_gate_kernel(const float* __restrict__ probs, const int* __restrict__ win_offsets, int n_streams,
+                                long long* __restrict__ state, const double* __restrict__ min_silence,
+                                float threshold, long long speech_pad, long long* __restrict__ events) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_streams) return;
+  long long triggered = state[3 * s], temp_end = state[3 * s + 1], cur = state[3 * s + 2];
+  const double min_sil = min_silence[s];
+  bool has_ret = false, has_start = false, has_end = false;  // `ret` of FixedVADIterator.__call__
+  long long start = 0, end = 0;
+  for (int w = win_offsets[s]; w < win_offsets[s + 1]; ++w) {
+    const float p = probs[w];
+    cur += 512;
+    bool r_start = false, r_end = false;
+    long long rs = 0, re = 0;
+    if (p >= threshold && temp_end) temp_end = 0;
+    if (p >= threshold && !triggered) {
+      triggered = 1;
+      r_start = true;
+      rs = cur - speech_pad - 512;
+    } else if (p < threshold - 0.15f && triggered) {
+      if (!temp_end) temp_end = cur;
+      if (!((double)(cur - temp_end) < min_sil)) {
+        r_end = true;
+        re = temp_end + speech_pad - 512;
+        temp_end = 0;
+        triggered = 0;
+      }
+    }
+    if (!has_ret) {  // ret is None: take r as it is (possibly None)
+      if (r_start || r_end) {
+        has_ret = true;
+        has_start = r_start; start = rs;
+        has_end = r_end; end = re;
+      }
+    } else if (r_start || r_end) {
+      if (r_end) { has_end = true; end = re; }                      // the latter end
+      if (r_start && has_end) has_end = false;                      // a new start merges the segments
+    }
+  }
+  state[3 * s] = triggered; state[3 * s + 1] = temp_end; state[3 * s + 2] = cur;
+  events[4 * s] = has_start; events[4 * s + 1] = start; events[4 * s + 2] = has_end; events[4 * s + 3] = end;
+}
+
+void vad_window_energy_launch(const float* windows, int n_windows, float k, float* probs, cudaStream_t stream) {
+  if (n_windows <= 0) return;
+  vad_window_energy_kernel<<<cdiv(n_windows, 8), 256, 0, stream>>>(windows, n_windows, k, probs);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+void vad_gate_launch(const float* probs, const int* win_offsets, int n_streams, long long* state,
+                     const double* min_silence, float threshold, long long speech_pad, long long* events,
+                     cudaStream_t stream) {
+  if (n_streams <= 0) return;
+  vad_gate_kernel<<<cdiv(n_streams, 128), 128, 0, stream>>>(probs, win_offsets, n_streams, state, min_silence, threshold,
+                                                            speech_pad, events);
+  B200W_COUNT_LAUNCH();
+  B200W_CHECK_CUDA(cudaGetLastError());
+}
+
 }  // namespace b200w

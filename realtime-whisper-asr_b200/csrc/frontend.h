@@ -26,4 +26,11 @@ void bandpass_filtfilt_launch(const float* audio, const long long* offsets, int 
                               float* out, float* rpad_scratch, cudaStream_t stream);
 static constexpr int BANDPASS_PAD = 27;
 
+// Batched VAD gate (DynamicVADIterator / upstream VADIterator semantics): windows fp32 [n_windows][512];
+// win_offsets int32 [n_streams + 1]; state int64 [n_streams][3]; events int64 [n_streams][4].
+void vad_window_energy_launch(const float* windows, int n_windows, float k, float* probs, cudaStream_t stream);
+void vad_gate_launch(const float* probs, const int* win_offsets, int n_streams, long long* state,
+                     const double* min_silence, float threshold, long long speech_pad, long long* events,
+                     cudaStream_t stream);
+
 }  // namespace b200w

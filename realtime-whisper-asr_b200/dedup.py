@@ -70,8 +70,18 @@ class B200AudioDeduplicator:
         self._clean_history(current_time)
         try:
             feats = self._extract_features(audio, sample_rate)
-        except Exception:
-            self.stats["passed"] += 1  # conservative: never drop audio on a failure
+        except Exception as e:
+            # conservative like the reference (never drop audio on a failure), but never silently: chunks longer
+            # than the shared-memory DFT takes (55 296 samples = 3.46 s; the reference's callers pass 1-2 s buffers,
+            # 一键实时识别麦克风.py:1750-1760) are counted and reported once
+            self.stats["passed"] += 1
+            self.stats["feature_failures"] = self.stats.get("feature_failures", 0) + 1
+            if not getattr(self, "_warned_failure", False):
+                self._warned_failure = True
+                import logging
+                logging.getLogger("b200w").warning(
+                    "audio dedup: feature extraction failed for a %.2f s chunk (%s); such chunks pass unchecked",
+                    audio_length, e)
             return False, None, None
         return self._decide(feats, current_time, audio_length)
 
