@@ -170,3 +170,44 @@ def test_word_timing_paths_match_oracle_sweep(setup, cuda_device):
     print(f"{size}: DTW path identical on {same}/{total} chunks; worst boundary displacement {worst} frames")
     assert same >= 0.8 * total, f"DTW path identical on only {same}/{total} chunks"
     assert worst <= 1, f"a word boundary moved by {worst} frames"
+
+
+@pytest.mark.parametrize("size", ["tiny", "base", "small"])
+def test_beam5_tokens_vs_oracle_reported(size, cuda_device):
+    """Beam search (beam 5, patience 1, length penalty 1: the reference's default call, asr_components.py:281) against
+    the oracle's beam search on the same chunks (fixtures parity_<size>_beam5.json).  The north star's hard bar is the
+    greedy one above; beam rankings compare cumulative log-probabilities of near-tied hypotheses, so a bf16 engine may
+    legitimately return another hypothesis of (nearly) the same score.  Every divergence is listed with both scores;
+    asserted: >= 80 % of the chunks token-identical, and a divergent chunk's score within 2 % of the oracle's."""
+    p = os.path.join(GOLD, f"parity_{size}_beam5.json")
+    if not os.path.exists(p):
+        pytest.skip(f"{p} not generated")
+    gold = json.load(open(p))
+    md = W.MODEL_DIMS[size]
+    model = B200WhisperModel(size, state_dict=W.synthetic_state_dict(md, seed=0), dims=md, max_batch=8, max_beam=5)
+    tk = Tokenizer(md.n_vocab, True, language="en")
+    opts = DecodeOptions(beam_size=5, eot=tk.eot, sot=tk.sot, no_speech=tk.no_speech, no_timestamps=tk.no_timestamps,
+                         timestamp_begin=tk.timestamp_begin, suppress_ids=tk.suppressed_tokens([-1]),
+                         blank_ids=tk.blank_tokens())
+    chunks = gold["chunks"]
+    same = 0
+    for c0 in range(0, len(chunks), model.max_batch):
+        sel = chunks[c0:c0 + model.max_batch]
+        auds = [speech_like(c["seed"], c["seconds"]) for c in sel]
+        dev, offs = FE.upload_audio(auds, cuda_device)
+        win = FE.pack_windows(FE.log_mel(dev, offs, md.n_mels), list(range(len(sel))), [0] * len(sel))
+        ckv = model.engine.cross_kv(model.engine.encode(win))
+        prompts = [prompt_tokens(Tokenizer(md.n_vocab, True, language=c["language"]), c["prompt"]) for c in sel]
+        for c, res in zip(sel, model.engine.decode(ckv, prompts, opts)):
+            if res.tokens == c["tokens"]:
+                same += 1
+                continue
+            n, a, b = _diverge(res.tokens, c["tokens"])
+            sg = res.sum_logprob / max(1, len(res.tokens))
+            so = c["sum_logprob"] / max(1, len(c["tokens"]))
+            print(f"{size} beam-5 chunk {c['k']}: diverges at {n}: gpu {a} vs oracle {b}; score/len gpu {sg:.4f} oracle {so:.4f}")
+            assert abs(sg - so) <= 0.02 * max(1.0, abs(so)) + 0.02, "a divergent beam result must be a near-tie"
+    print(f"{size} beam 5: {same}/{len(chunks)} chunks token-identical")
+    assert same >= 0.8 * len(chunks)
+    for e in model.engines:
+        e.close()
