@@ -152,6 +152,32 @@ int b200w_cross_attention_flash(const void* cross_kv_dev, int n_streams, int n_l
                                 const int32_t* seg_start_dev, const int32_t* seg_count_dev, int n_segs,
                                 int max_seg_rows, void* out_dev, void* stream);
 
+/* Decode-step self-attention (csrc/attention.cu, qkv_attn_kernel): split-K partial sums of the fused QKV
+ * projection -> bias, bf16 -> the row's new key / value into the paged cache -> attention over the row's history
+ * (through its page-table row) plus its own position.  rows_per_group consecutive rows (the beams of one stream,
+ * <= 8) are handled by one CTA per head.
+ *   partial_dev fp32 [n_splits][rows][3d]   bias_dev fp32 [3d]   slot_dev int32 [rows] slot of the row's own token
+ *   kpool_dev / vpool_dev bf16 [slots][d]   table_dev int32 [table rows][table_stride] position -> slot
+ *   trow_dev int32 [rows] page-table row    kvlen_dev int32 [rows] visible keys INCLUDING the row's own position
+ *   out_dev bf16 [rows][d]                  max_len >= every kvlen */
+int b200w_step_self_attention(const float* partial_dev, int n_splits, const float* bias_dev, int rows, int d,
+                              int n_heads, const int32_t* slot_dev, void* kpool_dev, void* vpool_dev,
+                              const int32_t* table_dev, int table_stride, const int32_t* trow_dev,
+                              const int32_t* kvlen_dev, int max_len, int rows_per_group, void* out_dev, void* stream);
+
+/* Fused logit rules + log-softmax + top-k of the decode step (csrc/kernels.cu, sample_row_kernel): per row, the
+ * static suppress mask (bit0 always, bit1 at the first sampled position), Whisper's timestamp rules driven by
+ * state[row] = (flags, lowest admissible timestamp id, 0, 0) with flags bit0 rules on, bit1 first position, bit2
+ * no timestamp may follow, bit3 only timestamps / EOT may follow; log-probabilities renormalised over the
+ * timestamps when their total mass beats every text token; the k best (ties: lower id) -> ids / logprobs [rows][k].
+ *   logits_dev fp32 [rows][ld] (ld % 8 == 0)   mask_dev uint8 [n_vocab]   state_dev int32 [rows][4]
+ *   streaming != 0 selects the kernel that streams the row from global memory three times (fallback for rows that
+ *   do not fit in shared memory); both give bit-identical results. */
+int b200w_sample_topk(const float* logits_dev, int rows, int ld, int n_vocab, const uint8_t* mask_dev,
+                      const int32_t* state_dev, int eot, int no_timestamps, int timestamp_begin,
+                      int max_initial_ts, int k, int32_t* out_ids_dev, float* out_logprobs_dev, int streaming,
+                      void* stream);
+
 /* conv1d (kernel 3, padding 1, stride 1 or 2) as implicit GEMM over time-major activations:
  * x bf16 [B][T][C] -> GELU(conv(x) + bias) (+ addend fp32 [T_out][N], e.g. positions) ->
  * out [B][T_out][N] bf16 or fp32.  w bf16 [N][3*C] tap-major.  C % 64 == 0. */

@@ -59,6 +59,8 @@ SIGNATURES = {
     "b200w_vad_gate": (_i, [_vp, _vp, _i, _vp, _vp, _f, _i64, _vp, _vp]),
     "b200w_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _vp]),
     "b200w_skinny_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _vp]),
+    "b200w_step_self_attention": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "b200w_sample_topk": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "b200w_cross_attention_tc_scratch_bytes": (C.c_int64, []),
     "b200w_cross_attention_tc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _f, _vp, _i, _vp]),
     "b200w_cross_attention_flash": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),

@@ -13,6 +13,7 @@
 #include "dstep.h"
 #include "frontend.h"
 #include "gemm.h"
+#include "kernels.h"
 #include "skinny.h"
 
 namespace b200w {
@@ -206,6 +207,38 @@ int b200w_skinny_gemm(const void* X_dev, const void* W_dev, const float* bias_de
   d.tile_rows = (splits >> 8) == 64 ? 64 : 128;  // test hook: bits 8.. of `splits` select 64-row tiles
   d.split_stride = (int64_t)M * ldo;
   skinny_gemm(d, static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
+int b200w_step_self_attention(const float* partial_dev, int n_splits, const float* bias_dev, int rows, int d,
+                              int n_heads, const int32_t* slot_dev, void* kpool_dev, void* vpool_dev,
+                              const int32_t* table_dev, int table_stride, const int32_t* trow_dev,
+                              const int32_t* kvlen_dev, int max_len, int rows_per_group, void* out_dev, void* stream) {
+  B200W_API_BEGIN
+  QkvAttnParams qa;
+  qa.partial = partial_dev; qa.n_splits = n_splits; qa.split_stride = (long long)rows * 3 * d;
+  qa.bias = bias_dev; qa.d = d; qa.slot = slot_dev;
+  qa.kpool = static_cast<bf16*>(kpool_dev); qa.vpool = static_cast<bf16*>(vpool_dev);
+  qa.table = table_dev; qa.table_stride = table_stride; qa.trow = trow_dev; qa.kvlen = kvlen_dev;
+  qa.out = static_cast<bf16*>(out_dev); qa.out_stride = d; qa.scale = 0.125f; qa.max_len = max_len;
+  qa.rows_per_cta = rows_per_group;
+  qkv_attention(qa, rows, n_heads, static_cast<cudaStream_t>(stream));
+  B200W_API_END
+}
+
+int b200w_sample_topk(const float* logits_dev, int rows, int ld, int n_vocab, const uint8_t* mask_dev,
+                      const int32_t* state_dev, int eot, int no_timestamps, int timestamp_begin,
+                      int max_initial_ts, int k, int32_t* out_ids_dev, float* out_logprobs_dev, int streaming,
+                      void* stream) {
+  B200W_API_BEGIN
+  B200W_REQUIRE(ld % 8 == 0 && ld >= n_vocab, "sample_topk: ld must be a multiple of 8 and >= n_vocab");
+  SampleParams sp;
+  sp.logits = logits_dev; sp.ld = ld; sp.n_vocab = n_vocab; sp.mask = mask_dev;
+  sp.state = reinterpret_cast<const int4*>(state_dev);
+  sp.eot = eot; sp.no_timestamps = no_timestamps; sp.timestamp_begin = timestamp_begin;
+  sp.max_initial_ts = max_initial_ts; sp.k = k;
+  sp.out_ids = out_ids_dev; sp.out_logprobs = out_logprobs_dev;
+  sample_topk(sp, rows, static_cast<cudaStream_t>(stream), streaming != 0);
   B200W_API_END
 }
 

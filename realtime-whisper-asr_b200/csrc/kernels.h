@@ -43,7 +43,7 @@ struct SampleParams {
   int* out_ids;         // [rows][k]
   float* out_logprobs;  // [rows][k]
 };
-void sample_topk(const SampleParams& p, int rows, cudaStream_t stream);
+void sample_topk(const SampleParams& p, int rows, cudaStream_t stream, bool streaming = false);
 
 void token_probs(const float* logits, int ld, int n_vocab, const int* rows, const int* tok,
                  const int* ids, int n_ids, float* out, int n_rows, cudaStream_t stream);
