@@ -189,6 +189,11 @@ int b200w_conv1d_k3(const void* x_dev, const void* w_dev, const float* bias_dev,
 int b200w_enc_attention(const void* qkv_dev, int B, int T, int d, int n_heads, void* out_dev,
                         void* stream);
 
+/* Profiling aid: with B200W_ENC_ATTN_DBG=2 in the environment one CTA of the encoder attention kernel records
+ * clock64 stamps of its pipeline phases, [role 0..3][key block 0..31][stamp 0..7] (roles: softmax tile 0 / 1, MMA
+ * issuer, TMA producer).  Copies the first n values to host_out. */
+int b200w_enc_attention_trace_read(int64_t* host_out, int n);
+
 /* ---------------------------------------------------------------- engine --------------------- */
 
 typedef struct b200w_engine b200w_engine;

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200whisper.so")
+# B200W_LIB: another build of the same library (A/B timing of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("B200W_LIB") or os.path.join(_HERE, "lib", "libb200whisper.so")
 
 _lib = None
 
@@ -66,6 +67,7 @@ SIGNATURES = {
     "b200w_cross_attention_flash": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "b200w_conv1d_k3": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200w_enc_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "b200w_enc_attention_trace_read": (_i, [_vp, _i]),
     "b200w_engine_create": (_i, [C.POINTER(ModelConfig), C.POINTER(_vp)]),
     "b200w_engine_destroy": (_i, [_vp]),
     "b200w_engine_set_weight": (_i, [_vp, C.c_char_p, _vp, _i64, _i]),

@@ -242,6 +242,12 @@ int b200w_sample_topk(const float* logits_dev, int rows, int ld, int n_vocab, co
   B200W_API_END
 }
 
+int b200w_enc_attention_trace_read(int64_t* host_out, int n) {
+  B200W_API_BEGIN
+  enc_attention_trace_read(reinterpret_cast<long long*>(host_out), n);
+  B200W_API_END
+}
+
 int64_t b200w_cross_attention_tc_scratch_bytes(void) { return (int64_t)cross_attention_tc_scratch_bytes(); }
 
 int b200w_cross_attention_tc(const void* cross_kv_dev, int n_streams, int n_layers, int layer, int n_heads, int len,

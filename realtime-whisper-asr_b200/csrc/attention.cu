@@ -37,6 +37,7 @@ struct EncAttnParams {
   const int* seg_count;
   const int* row_stream;
   int blocks_per_stream, layer_block0, n_heads;
+  int dbg = 0;  // B200W_ENC_ATTN_DBG: bit1 one CTA records a phase trace
 };
 
 // KT = keys per inner block (64 or 128).  Smaller blocks mean less shared memory and TMEM per CTA,
@@ -246,6 +247,327 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// ---- Second flash kernel (encoder self-attention and the flash cross attention), round 2.
+// The kernel above is one warpgroup doing everything in lock step: per 64-key block two CTA-wide barriers, the O
+// tile read back from TMEM and rescaled in registers (a third of its instruction stream), MMAs issued by a softmax
+// thread.  ncu: tensor pipe 21.5 % active, issue slots 47.5 % busy; 783 us at the bench shape.  This one:
+//  * warp-specialised: warps 0-3 softmax (thread = query row = TMEM lane), warp 4 TMA producer (4-stage K and V
+//    rings), warp 5 MMA issuer; everything hands over through mbarriers, no CTA-wide barrier inside the loop.
+//    The issuer runs its loop with the WHOLE warp and elects a lane only around the tcgen05 instructions, so that
+//    descriptors live in uniform registers (a single divergent lane spent ~70 cycles per MMA on R2UR chains);
+//  * S double-buffered in TMEM: S(j+1) = Q K_{j+1}^T runs on the tensor pipe while the softmax of block j runs;
+//    issue order S(0) S(1) PV(0) S(2) PV(1) ...;
+//  * O stays in TMEM for the whole key loop (the P.V MMAs accumulate) and is rescaled LAZILY: probabilities are
+//    taken relative to a reference maximum that only moves when the running maximum exceeds it by more than 2^8
+//    (exact arithmetic: l and O use the same reference; the result is O / l whatever the reference was);
+//  * the A operands of both products live in TENSOR MEMORY.  With every operand in shared memory (first versions of
+//    this kernel: 660-700 us whatever the softmax did, phase trace: ~70 cycles per 128x64x16 MMA instead of 32) the
+//    kernel is shared-memory-bandwidth bound: per 64-key block the MMAs fetch Q (16 KB, again every block) + K (8 KB)
+//    and P (16 KB) + V (8 KB), the softmax stores P (16 KB), TMA writes K and V (16 KB): 80 KB at 128 B / clock =
+//    640 cycles per block against 262 cycles of tensor work.  Q is copied once into TMEM (bf16 pairs, 32 columns)
+//    and P is written by tcgen05.st over the first 32 columns of the S buffer it was computed from; the MMAs read
+//    only K and V from shared memory (16 KB per block);
+//  * row maximum and row sum as four independent chains (FMNMX3, FADD2), scale-and-shift as FFMA2;
+//  * what is left is the exponential: 64 ex2 per row per block = 512 MUFU cycles per CTA-block against 262 tensor
+//    cycles (head dim 64), so one exponential in PE is evaluated on the FMA pipe (ex2_poly) instead.
+// 2 CTAs per SM (256 TMEM columns, 82 KB shared memory each).  Measured (tools/enc_attn_bench.py, 32 x 1500 x 20
+// heads): 783 us -> 495 us (744 TFLOP/s).  Also tried and dropped: two query tiles per CTA sharing the K / V stream
+// (lock-step softmax phases, 770 us with operands in shared memory) and two threads per query row (no gain).
+// Phase trace of one CTA (B200W_ENC_ATTN_DBG=2): clock64 stamps, [role][block][stamp]
+__device__ long long g_enc_trace[4 * 32 * 8];
+template <int PE>  // every PE-th exponential on the FMA pipe (0 = none)
+__global__ void __launch_bounds__(192, 2)
+enc_attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 const EncAttnParams p) {
+  constexpr int KT = 64, NS = 4;
+  constexpr int KV_BYTES = KT * HD * 2;  // one K or V block (8 KB)
+  constexpr uint32_t TMEM_COLS = 256;    // S0 / P0 | S1 / P1 | O | Q (32 columns of bf16 pairs)
+  constexpr float TAU = 8.0f;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;        // [NS]
+  uint8_t* sV = sK + NS * KV_BYTES;     // [NS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * KV_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 4 * NS + 6);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
+  const uint32_t barQ = smem_u32(bars), barQT = smem_u32(bars + 1);         // Q in shared memory / in tensor memory
+  auto barK = [&](int s) { return smem_u32(bars + 2 + s); };                // K block landed
+  auto barV = [&](int s) { return smem_u32(bars + 2 + NS + s); };           // V block landed
+  auto barKfree = [&](int s) { return smem_u32(bars + 2 + 2 * NS + s); };   // S MMAs of the block done
+  auto barVfree = [&](int s) { return smem_u32(bars + 2 + 3 * NS + s); };   // P.V MMAs of the block done
+  auto barS = [&](int s) { return smem_u32(bars + 2 + 4 * NS + s); };       // S = Q K^T complete
+  auto barP = [&](int s) { return smem_u32(bars + 2 + 4 * NS + 2 + s); };   // P written by all 128 rows
+  auto barO = [&](int s) { return smem_u32(bars + 2 + 4 * NS + 4 + s); };   // O += P V complete
+  const bool cross = p.seg_start != nullptr;
+  int row0 = 0, n_rows = p.T;
+  if (cross) {
+    pdl_trigger();
+    pdl_wait();
+    row0 = p.seg_start[b];
+    n_rows = p.seg_count[b];
+    if (q0 >= n_rows) return;  // before any barrier / TMEM use: whole CTA leaves
+  }
+  if (tid == 0) {
+    mbar_init(barQ, 1);
+    mbar_init(barQT, 128);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(barK(s), 1);
+      mbar_init(barV(s), 1);
+      mbar_init(barKfree(s), 1);
+      mbar_init(barVfree(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(barS(s), 1);
+      mbar_init(barP(s), 128);
+      mbar_init(barO(s), 1);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_O = tmem_base + 2 * KT, tmem_Q = tmem_base + 3 * KT;
+  const int nblk = (p.T + KT - 1) / KT;
+  const bool tracing = (p.dbg & 2) && blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 1;
+  auto stamp = [&](int role, int j, int k) {
+    if (tracing && j < 32 && (role < 2 || lane == 0)) g_enc_trace[(role * 32 + j) * 8 + k] = clock64();
+  };
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int colQ = h * HD;
+      const int colK = cross ? 0 : p.d + h * HD, colV = cross ? 0 : 2 * p.d + h * HD;
+      const int rowQ = row0 + q0, zQ = cross ? 0 : b;
+      int zK = b, zV = b;
+      if (cross) {
+        zK = p.row_stream[row0] * p.blocks_per_stream + p.layer_block0 + h;
+        zV = zK + p.n_heads;
+      }
+      mbar_arrive_expect_tx(barQ, TILE_BYTES);
+      tma_load_3d(smem_u32(sQ), &tmQ, barQ, colQ, rowQ, zQ);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % NS, n = j / NS;
+        if (j >= NS) mbar_wait_backoff(barKfree(s), (n - 1) & 1);
+        mbar_arrive_expect_tx(barK(s), KV_BYTES);
+        tma_load_3d(smem_u32(sK + s * KV_BYTES), &tmKV, barK(s), colK, j * KT, zK);
+        if (j >= NS) mbar_wait_backoff(barVfree(s), (n - 1) & 1);
+        mbar_arrive_expect_tx(barV(s), KV_BYTES);
+        tma_load_3d(smem_u32(sV + s * KV_BYTES), &tmKV, barV(s), colV, j * KT, zV);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    constexpr uint32_t idescS = make_idesc_bf16(128, KT, 0, 0);  // Q (TMEM) x K (K-major)
+    constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);  // P (TMEM) x V (MN-major)
+    auto pv = [&](int i) {  // O += P(i) V(i)
+      const int sb = i & 1, nb = i >> 1, s = i % NS, n = i / NS;
+      mbar_wait_backoff(barV(s), n & 1);
+      stamp(2, i, 3);
+      mbar_wait_backoff(barP(sb), nb & 1);
+      stamp(2, i, 4);
+      tc_fence_after();
+      const uint64_t vd = make_sw128_desc(smem_u32(sV + s * KV_BYTES));
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k)  // P: 16 keys = 8 columns; V: +16 key rows = +2048 B
+          tc_mma_bf16_ta(tmem_O, tmem_base + sb * KT + 8 * k, vd + 128 * k, idescO, (i > 0 || k > 0) ? 1u : 0u);
+        tc_commit(barO(sb));
+        tc_commit(barVfree(s));
+      }
+      __syncwarp();
+      stamp(2, i, 6);
+    };
+    mbar_wait_backoff(barQT, 0);
+    tc_fence_after();
+    for (int j = 0; j < nblk; ++j) {
+      const int sb = j & 1, s = j % NS, n = j / NS;
+      stamp(2, j, 0);
+      mbar_wait_backoff(barK(s), n & 1);
+      stamp(2, j, 1);
+      tc_fence_after();
+      // (S buffer sb holds P(j-2) until PV(j-2) has read it: that MMA was issued before this one, and MMAs execute
+      // in issue order)
+      const uint64_t kd = make_sw128_desc(smem_u32(sK + s * KV_BYTES));
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) tc_mma_bf16_ta(tmem_base + sb * KT, tmem_Q + 8 * k, kd + 2 * k, idescS, k != 0);
+        tc_commit(barS(sb));
+        tc_commit(barKfree(s));
+      }
+      __syncwarp();
+      stamp(2, j, 2);
+      if (j > 0) pv(j - 1);
+    }
+    pv(nblk - 1);
+  } else {
+    // ------------------------------------------------------------------ softmax: thread = query row = TMEM lane
+    const int r = tid;
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    {  // this row of Q: swizzled shared-memory tile -> 32 columns of bf16 pairs in tensor memory
+      mbar_wait(barQ, 0);
+      uint32_t qv[32];
+      const uint8_t* row = sQ + r * 128;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const uint4 u = *reinterpret_cast<const uint4*>(row + ((cc ^ (r & 7)) << 4));
+        qv[4 * cc] = u.x; qv[4 * cc + 1] = u.y; qv[4 * cc + 2] = u.z; qv[4 * cc + 3] = u.w;
+      }
+      tmem_st32(tmem_Q + lane_sel, qv);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(barQT);
+    }
+    float m_ref = -INFINITY, l_run = 0.f;  // reference maximum (log2 domain) of every probability so far
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1, n = j >> 1;
+      if (r == 0) stamp(0, j, 0);
+      mbar_wait(barS(s), n & 1);
+      if (r == 0) stamp(0, j, 1);
+      tc_fence_after();
+      uint32_t v[64];
+      tmem_ld32(tmem_base + s * KT + lane_sel, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(tmem_base + s * KT + lane_sel + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld_wait();
+      if (r == 0) stamp(0, j, 2);
+      const int kv_valid = min(KT, p.T - j * KT);
+      if (kv_valid < KT) {  // ragged tail of the last block (uniform branch)
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= kv_valid) v[i] = 0xff800000u;  // -inf
+      }
+      float mxc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int o = 16 * c;
+        float m = fmax3(__uint_as_float(v[o]), __uint_as_float(v[o + 1]), __uint_as_float(v[o + 2]));
+#pragma unroll
+        for (int i = 3; i + 1 < 16; i += 2) m = fmax3(m, __uint_as_float(v[o + i]), __uint_as_float(v[o + i + 1]));
+        mxc[c] = fmaxf(m, __uint_as_float(v[o + 15]));
+      }
+      const float mxs = fmaxf(fmax3(mxc[0], mxc[1], mxc[2]), mxc[3]) * p.scale_log2e;
+      if (j == 0) {
+        m_ref = mxs;
+      } else {
+        const bool need = mxs > m_ref + TAU;
+        if (__any_sync(0xffffffffu, need)) {  // rare after the first blocks: rescale this warp's rows of O
+          mbar_wait(barO((j - 1) & 1), ((j - 1) >> 1) & 1);  // every P.V issued so far is complete
+          tc_fence_after();
+          const float alpha = need ? ex2_approx(m_ref - mxs) : 1.0f;
+#pragma unroll
+          for (int c0 = 0; c0 < HD; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_sel + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_sel + c0, o);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          if (need) m_ref = mxs;
+        }
+      }
+      uint32_t packed[32];
+      {
+        const unsigned long long sc2 = pack_f32x2(p.scale_log2e, p.scale_log2e), nm2 = pack_f32x2(-m_ref, -m_ref);
+        unsigned long long ls2[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          float x0, x1;
+          unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2), x0, x1);
+          const float p0 = (PE > 0 && (i % (PE > 0 ? PE : 1)) == 0) ? ex2_poly(x0) : ex2_approx(x0);
+          const float p1 = ex2_approx(x1);
+          ls2[(i >> 1) & 3] = fadd2(ls2[(i >> 1) & 3], pack_f32x2(p0, p1));
+          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+          packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+        }
+        float a, b2;
+        unpack_f32x2(fadd2(fadd2(ls2[0], ls2[1]), fadd2(ls2[2], ls2[3])), a, b2);
+        l_run += a + b2;
+      }
+      if (r == 0) stamp(0, j, 3);
+      // P over the first 32 columns of this block's S buffer (every S value of the row is in registers by now)
+      tmem_st32(tmem_base + s * KT + lane_sel, packed);
+      tmem_st_wait();
+      if (r == 0) stamp(0, j, 4);
+      tc_fence_before();
+      mbar_arrive(barP(s));
+      if (r == 0) stamp(0, j, 5);
+    }
+    mbar_wait(barO((nblk - 1) & 1), ((nblk - 1) >> 1) & 1);
+    tc_fence_after();
+    const int t = q0 + r;
+    const float inv = 1.0f / l_run;
+    bf16* dst = p.out + (cross ? (long long)(row0 + t) : (long long)b * p.T + t) * p.d + h * HD;
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_sel + c0, o);
+      tmem_ld_wait();
+      if (t < n_rows) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 u;
+          __nv_bfloat162* u2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            u2[i] = __floats2bfloat162_rn(__uint_as_float(o[c + 2 * i]) * inv, __uint_as_float(o[c + 2 * i + 1]) * inv);
+          *reinterpret_cast<uint4*>(dst + c0 + c) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+static constexpr int ENC4_SMEM = TILE_BYTES + 2 * 4 * (64 * HD * 2) + (2 + 4 * 4 + 6) * 8 + 16 + 1024;
+
+static int enc_attn_variant() {  // 0: first kernel (B200W_ENC_ATTN_V1=1), 4: the kernel above
+  static const int v = getenv("B200W_ENC_ATTN_V1") ? 0 : 4;
+  return v;
+}
+void enc_attention_trace_read(long long* host_out, int n) {
+  B200W_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_enc_trace, sizeof(long long) * std::min(n, 4 * 32 * 8)));
+}
+static int enc_attn_dbg() {
+  static const int v = getenv("B200W_ENC_ATTN_DBG") ? atoi(getenv("B200W_ENC_ATTN_DBG")) : 0;
+  return v;
+}
+static int enc_attn_pe() {
+  static const int v = getenv("B200W_ENC_ATTN_PE") ? atoi(getenv("B200W_ENC_ATTN_PE")) : 0;
+  return v;
+}
+template <typename... Args>
+static void launch_enc_attn4(bool pdl, int q_rows, int gy, int gz, cudaStream_t stream, Args&&... args) {
+  const dim3 grid(cdiv(q_rows, QT), gy, gz);
+  auto go = [&](auto kernel) {
+    ensure_dynamic_smem(kernel, ENC4_SMEM);
+    if (pdl) launch_pdl(kernel, grid, dim3(192), (size_t)ENC4_SMEM, stream, args...);
+    else kernel<<<grid, 192, ENC4_SMEM, stream>>>(args...);
+  };
+  switch (enc_attn_pe()) {
+    case 4: go(enc_attn4_kernel<4>); break;
+    case 8: go(enc_attn4_kernel<8>); break;
+    default: go(enc_attn4_kernel<0>); break;
+  }
+}
+
 // ---- optional per-launch timing of the encoder attention (bench.py's second tensor roofline): CUDA events around
 // every launch on the launching stream, read back after a synchronize.
 struct AttnProfSlot {
@@ -302,7 +624,13 @@ static void launch_enc_attn(const bf16* qkv, int B, int T, int d, int n_heads, b
     ps = attn_prof_slot(4.0 * (double)T * (double)T * (double)d * (double)B);  // S = Q K^T and O = P V: 2 x 2 T^2 d
     B200W_CHECK_CUDA(cudaEventRecord(ps->beg, stream));
   }
-  enc_attn_kernel<KT, CTAS><<<dim3(cdiv(T, QT), n_heads, B), 128, smem_bytes, stream>>>(tmQ, tmKV, p);
+  if (enc_attn_variant() >= 2) {
+    make_tmap_bf16_3d(&tmKV, qkv, 3 * (uint64_t)d, T, B, 3 * (uint64_t)d, (uint64_t)T * 3 * d, HD, 64);
+    p.dbg = enc_attn_dbg();
+    launch_enc_attn4(false, T, n_heads, B, stream, tmQ, tmKV, p);
+  } else {
+    enc_attn_kernel<KT, CTAS><<<dim3(cdiv(T, QT), n_heads, B), 128, smem_bytes, stream>>>(tmQ, tmKV, p);
+  }
   if (ps) B200W_CHECK_CUDA(cudaEventRecord(ps->end, stream));
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
@@ -329,8 +657,12 @@ void cross_attention_flash(const bf16* cross_kv, int n_streams, int n_layers, in
   ensure_dynamic_smem(enc_attn_kernel<64, 3>, smem_bytes);
   EncAttnParams p{len, d, 0.125f * 1.4426950408889634f, out, seg_start, seg_count, row_stream,
                   n_layers * 2 * n_heads, 2 * layer * n_heads, n_heads};
-  launch_pdl(enc_attn_kernel<64, 3>, dim3(cdiv(max_seg_rows, QT), n_heads, n_segs), dim3(128), (size_t)smem_bytes, stream,
-             tmQ, tmKV, p);
+  if (enc_attn_variant() >= 2) {
+    p.dbg = enc_attn_dbg();
+    launch_enc_attn4(true, max_seg_rows, n_heads, n_segs, stream, tmQ, tmKV, p);
+  } else
+    launch_pdl(enc_attn_kernel<64, 3>, dim3(cdiv(max_seg_rows, QT), n_heads, n_segs), dim3(128), (size_t)smem_bytes, stream,
+               tmQ, tmKV, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }
@@ -484,7 +816,7 @@ __device__ __forceinline__ int hist_r_dyn(const int (&hist_r)[GM], int g) {
 
 template <int NT, int GM, int MIN_CTAS>
 __global__ void __launch_bounds__(NT, MIN_CTAS) qkv_attn_kernel(const QkvAttnParams p) {
-  constexpr int NW = NT / 32, NGRP = NT / 8, UB = 8;
+  constexpr int NW = NT / 32, UB = 8;
   extern __shared__ float s_dyn[];  // [G][max_len] page table (int) | [G][max_len] scores / probabilities
   __shared__ __align__(16) float s_q[GM][HD], s_k[GM][HD], s_v[GM][HD];
   __shared__ __align__(16) float s_acc[NW][GM][HD];
@@ -1304,7 +1636,8 @@ cross_attn_sp_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {  // ---------------- MMA issuer
+    {  // ---------------- MMA issuer: the whole warp runs the loop (warp-uniform state in uniform registers), an
+       // elected lane issues -- a single divergent lane paid a chain of R2UR moves per MMA
       constexpr uint32_t idescS = make_idesc_bf16(128, 16, 0, 0);  // K (K-major) x Q (K-major)
       constexpr uint32_t idescO = make_idesc_bf16(128, 64, 0, 1);  // P (K-major) x V (MN-major)
       uint32_t slot = 0, phase = 0, g0 = 0;
@@ -1322,11 +1655,14 @@ cross_attn_sp_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
             mbar_wait(bar_sf0 + 8 * ss, (us & 1u) ^ 1u);
             tc_fence_after();
             const uint64_t kd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_S + 16 * ss, kd + 2 * k, qd + 2 * k, idescS, k != 0);
-            tc_commit(empty0 + 8 * slot);
-            tc_commit(bar_s0 + 8 * ss);
-            if (j == nt - 1) tc_commit(bar_qf0 + 8 * par);
+              for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem_S + 16 * ss, kd + 2 * k, qd + 2 * k, idescS, k != 0);
+              tc_commit(empty0 + 8 * slot);
+              tc_commit(bar_s0 + 8 * ss);
+              if (j == nt - 1) tc_commit(bar_qf0 + 8 * par);
+            }
+            __syncwarp();
             if (++slot == XS_RING) { slot = 0; phase ^= 1; }
           }
           if (j >= XS_LA) {  // O += P_jj V_jj
@@ -1337,17 +1673,20 @@ cross_attn_sp_kernel(const __grid_constant__ CUtensorMap tmKV, const CrossTcPara
             mbar_wait(full0 + 8 * slot, phase);
             tc_fence_after();
             const uint64_t vd = make_sw128_desc(smem_u32(ring + slot * TILE_BYTES));
+            const uint64_t pd0 = make_sw128_desc(smem_u32(sP + ps * 2048)), pd1 = make_sw128_desc(smem_u32(sP + ps * 2048 + 1024));
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t pd = make_sw128_desc(smem_u32(sP + (ps * 2 + (k >> 2)) * 1024)) + 2 * (k & 3);
-              tc_mma_bf16(d_o, pd, vd + 128 * k, idescO, (jj | k) != 0);
+              for (int k = 0; k < 8; ++k)
+                tc_mma_bf16(d_o, (k < 4 ? pd0 : pd1) + 2 * (k & 3), vd + 128 * k, idescO, (jj | k) != 0);
+              tc_commit(empty0 + 8 * slot);
+              tc_commit(bar_pf0 + 8 * ps);
             }
-            tc_commit(empty0 + 8 * slot);
-            tc_commit(bar_pf0 + 8 * ps);
+            __syncwarp();
             if (++slot == XS_RING) { slot = 0; phase ^= 1; }
           }
         }
-        tc_commit(bar_o0 + 8 * par);
+        if (elect_one()) tc_commit(bar_o0 + 8 * par);
+        __syncwarp();
         g0 += nt;
       }
     }

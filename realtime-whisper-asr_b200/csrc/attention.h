@@ -34,6 +34,8 @@ struct DecAttnParams {
   int probs_stride = 0;
 };
 void dec_attention(const DecAttnParams& p, int n_heads, cudaStream_t stream);
+// phase trace of one CTA of the encoder attention kernel (B200W_ENC_ATTN_DBG=2): [role][block][stamp] clock64 values
+void enc_attention_trace_read(long long* host_out, int n);
 
 // Decode steps: split-K QKV partial sums -> (bias, bf16) -> new K/V into the cache + self-attention of the row.
 struct QkvAttnParams {
