@@ -601,7 +601,7 @@ def run_b200(args, rank, world, local):
                      "share_of_step": tms.value / dev_ms if dev_ms else None,
                      "timing": "CUDA events around every launch inside the timed region"}
     a_ach = (afl.value / 1e12) / (ams.value / 1e3) if ams.value > 0 else None
-    roofline_attn = {"bound": "tensor", "kernel": "enc_attn_kernel", "achieved": a_ach, "peak": peak_tf, "unit": "TFLOP/s",
+    roofline_attn = {"bound": "tensor", "kernel": "enc_attn4_kernel", "achieved": a_ach, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (a_ach / peak_tf) if a_ach else None, "traffic": None, "peak_source": peak_src,
                      "launches_timed": int(an.value), "kernel_ms_per_step": ams.value / args.steps,
                      "share_of_step": ams.value / dev_ms if dev_ms else None,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200W_ABI_VERSION 2
+#define B200W_ABI_VERSION 3
 
 const char* b200w_last_error(void);
 int b200w_abi_version(void);
@@ -172,11 +172,14 @@ int b200w_step_self_attention(const float* partial_dev, int n_splits, const floa
  * timestamps when their total mass beats every text token; the k best (ties: lower id) -> ids / logprobs [rows][k].
  *   logits_dev fp32 [rows][ld] (ld % 8 == 0)   mask_dev uint8 [n_vocab]   state_dev int32 [rows][4]
  *   streaming != 0 selects the kernel that streams the row from global memory three times (fallback for rows that
- *   do not fit in shared memory); both give bit-identical results. */
+ *   do not fit in shared memory); both give bit-identical results.
+ *   temperature > 0 (k must be 1): ONE token per row drawn from softmax(rule-masked logits / temperature) and its
+ *   log-probability under that distribution; the draw is a pure function of (seed, state[row][3] = sample stream,
+ *   state[row][2] = draw index). */
 int b200w_sample_topk(const float* logits_dev, int rows, int ld, int n_vocab, const uint8_t* mask_dev,
                       const int32_t* state_dev, int eot, int no_timestamps, int timestamp_begin,
                       int max_initial_ts, int k, int32_t* out_ids_dev, float* out_logprobs_dev, int streaming,
-                      void* stream);
+                      float temperature, uint32_t seed, void* stream);
 
 /* conv1d (kernel 3, padding 1, stride 1 or 2) as implicit GEMM over time-major activations:
  * x bf16 [B][T][C] -> GELU(conv(x) + bias) (+ addend fp32 [T_out][N], e.g. positions) ->
@@ -241,9 +244,15 @@ typedef struct b200w_decode_opts {
   int32_t n_suppress;
   const int32_t* blank_ids;      /* host, tokens suppressed at the first sampled position */
   int32_t n_blank;
+  /* temperature > 0: sampling instead of search (faster-whisper's fallback temperatures): best_of independent
+   * samples per chunk drawn from softmax(rule-masked logits / temperature), the one with the best length-normalised
+   * log-probability is returned; beam_size is ignored.  Draws are a pure function of (seed, chunk row, position). */
+  float temperature;             /* 0 = greedy / beam search */
+  int32_t best_of;               /* samples per chunk (<= max_beam) */
+  uint32_t seed;
 } b200w_decode_opts;
 
-/* Autoregressive decode of B chunks (greedy or beam search with Whisper's logit rules).
+/* Autoregressive decode of B chunks (greedy, beam search or temperature sampling, with Whisper's logit rules).
  *   prompts_host      int32 concatenated prompt tokens, prompt_lens_host int32 [B]
  *   tokens_out_host   int32 [B][max_out]   sampled tokens (without the prompt, without EOT)
  *   n_tokens_out_host int32 [B]

@@ -31,6 +31,7 @@ class DecodeOpts(C.Structure):
         ("no_timestamps", C.c_int32), ("timestamp_begin", C.c_int32),
         ("suppress_ids", C.POINTER(C.c_int32)), ("n_suppress", C.c_int32),
         ("blank_ids", C.POINTER(C.c_int32)), ("n_blank", C.c_int32),
+        ("temperature", C.c_float), ("best_of", C.c_int32), ("seed", C.c_uint32),
     ]
 
 
@@ -61,7 +62,7 @@ SIGNATURES = {
     "b200w_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _vp]),
     "b200w_skinny_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _i, _vp]),
     "b200w_step_self_attention": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
-    "b200w_sample_topk": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "b200w_sample_topk": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, C.c_uint32, _vp]),
     "b200w_cross_attention_tc_scratch_bytes": (C.c_int64, []),
     "b200w_cross_attention_tc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _f, _vp, _i, _vp]),
     "b200w_cross_attention_flash": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
@@ -98,7 +99,7 @@ def load(path: str | None = None):
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.b200w_abi_version() != 2:
+    if lib.b200w_abi_version() != 3:
         raise B200WError("libb200whisper.so ABI version mismatch")
     _lib = lib
     return lib

@@ -229,7 +229,7 @@ int b200w_step_self_attention(const float* partial_dev, int n_splits, const floa
 int b200w_sample_topk(const float* logits_dev, int rows, int ld, int n_vocab, const uint8_t* mask_dev,
                       const int32_t* state_dev, int eot, int no_timestamps, int timestamp_begin,
                       int max_initial_ts, int k, int32_t* out_ids_dev, float* out_logprobs_dev, int streaming,
-                      void* stream) {
+                      float temperature, uint32_t seed, void* stream) {
   B200W_API_BEGIN
   B200W_REQUIRE(ld % 8 == 0 && ld >= n_vocab, "sample_topk: ld must be a multiple of 8 and >= n_vocab");
   SampleParams sp;
@@ -238,6 +238,7 @@ int b200w_sample_topk(const float* logits_dev, int rows, int ld, int n_vocab, co
   sp.eot = eot; sp.no_timestamps = no_timestamps; sp.timestamp_begin = timestamp_begin;
   sp.max_initial_ts = max_initial_ts; sp.k = k;
   sp.out_ids = out_ids_dev; sp.out_logprobs = out_logprobs_dev;
+  sp.temperature = temperature; sp.seed = seed;
   sample_topk(sp, rows, static_cast<cudaStream_t>(stream), streaming != 0);
   B200W_API_END
 }

@@ -982,7 +982,7 @@ struct StreamState {
   std::vector<Finished> finished;
 };
 
-int4 sampling_state(const std::vector<int>& toks, const b200w_decode_opts& o) {
+int4 sampling_state(const std::vector<int>& toks, const b200w_decode_opts& o, int sample_stream = 0) {
   int flags = 0, ts_lo = 0;
   if (!o.without_timestamps) flags |= SF_RULES;
   const int n = (int)toks.size();
@@ -996,7 +996,7 @@ int4 sampling_state(const std::vector<int>& toks, const b200w_decode_opts& o) {
       if (toks[i] >= o.timestamp_begin) { last_stamp = toks[i]; break; }
     if (last_stamp >= 0) ts_lo = (last_ts && !pen_ts) ? last_stamp : last_stamp + 1;
   }
-  return make_int4(flags, ts_lo, 0, 0);
+  return make_int4(flags, ts_lo, (int)toks.size(), sample_stream);  // .z / .w: the sampler's draw index and stream
 }
 
 double norm_score(double cum, int len, float lp) {
@@ -1014,15 +1014,18 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
   std::lock_guard<std::mutex> engine_lock(e->mu);
   B200W_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch out of range");
   B200W_REQUIRE(opts && opts->beam_size >= 1 && opts->beam_size <= e->cfg.max_beam, "beam size out of range");
+  const bool sampling = opts->temperature > 0.f;
+  if (sampling) B200W_REQUIRE(opts->best_of >= 1 && opts->best_of <= e->cfg.max_beam, "best_of out of range");
   // everything below runs on the engine's own stream, ordered after the caller's stream
   cudaStream_t s = e->own_stream;
   B200W_CHECK_CUDA(cudaEventRecord(e->join_event, static_cast<cudaStream_t>(stream)));
   B200W_CHECK_CUDA(cudaStreamWaitEvent(s, e->join_event, 0));
   const b200w_decode_opts& o = *opts;
-  const int K = o.beam_size, k_top = K == 1 ? 1 : 2 * K;
+  // sampling: the K rows of a chunk are best_of independent samples (one token drawn per row per step)
+  const int K = sampling ? o.best_of : o.beam_size, k_top = (K == 1 || sampling) ? 1 : 2 * K;
   const bf16* ckv = static_cast<const bf16*>(cross_kv_dev);
   const int Tctx = e->Tctx;
-  const int max_cand = std::max(1, (int)lround(K * (double)o.patience));
+  const int max_cand = sampling ? K : std::max(1, (int)lround(K * (double)o.patience));
 
   // static masks: bit0 suppress list, bit1 first-position blanks
   {
@@ -1092,21 +1095,33 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
   for (int b = 0; b < B; ++b) no_speech_out_host[b] = e->h_out.as<float>()[b];
 
   // ---- first sampled position: one logits row per stream (rows 0..B of e->logits)
-  std::vector<int4> sstate(B);
-  for (int b = 0; b < B; ++b) sstate[b] = sampling_state({}, o);
+  // (sampling: K independent draws from the same row, the k-th launch reads the states / writes the outputs of
+  // entries [k B, (k + 1) B); the sampler's stream id of (chunk b, sample k) is b K + k, as in the steps)
+  const int n_first = sampling ? K : 1;
+  std::vector<int4> sstate((size_t)B * n_first);
+  for (int k = 0; k < n_first; ++k)
+    for (int b = 0; b < B; ++b) sstate[(size_t)k * B + b] = sampling_state({}, o, b * K + k);
   int4* state_dev = reinterpret_cast<int4*>(e->meta.p);  // reuse: the pass metadata is consumed
-  B200W_CHECK_CUDA(cudaMemcpyAsync(state_dev, sstate.data(), B * 16, cudaMemcpyHostToDevice, s));
+  B200W_CHECK_CUDA(cudaMemcpyAsync(state_dev, sstate.data(), sstate.size() * 16, cudaMemcpyHostToDevice, s));
   SampleParams sp;
   sp.logits = e->logits.as<float>(); sp.ld = e->ldv; sp.n_vocab = e->V;
   sp.mask = e->mask.as<unsigned char>(); sp.state = state_dev;
   sp.eot = o.eot; sp.no_timestamps = o.no_timestamps; sp.timestamp_begin = o.timestamp_begin;
   sp.max_initial_ts = o.max_initial_timestamp_index; sp.k = k_top;
   sp.out_ids = e->topk_ids.as<int>(); sp.out_logprobs = e->topk_lp.as<float>();
-  sample_topk(sp, B, s);
+  sp.temperature = sampling ? o.temperature : 0.f;
+  sp.seed = o.seed;
+  for (int k = 0; k < n_first; ++k) {
+    SampleParams spk = sp;
+    spk.state = state_dev + (size_t)k * B;
+    spk.out_ids = sp.out_ids + (size_t)k * B * k_top;
+    spk.out_logprobs = sp.out_logprobs + (size_t)k * B * k_top;
+    sample_topk(spk, B, s);
+  }
   int* h_ids = e->h_out.as<int>();
   float* h_lp = reinterpret_cast<float*>(h_ids + (size_t)B * K * MAX_TOPK);
-  B200W_CHECK_CUDA(cudaMemcpyAsync(h_ids, sp.out_ids, (size_t)B * k_top * 4, cudaMemcpyDeviceToHost, s));
-  B200W_CHECK_CUDA(cudaMemcpyAsync(h_lp, sp.out_logprobs, (size_t)B * k_top * 4, cudaMemcpyDeviceToHost, s));
+  B200W_CHECK_CUDA(cudaMemcpyAsync(h_ids, sp.out_ids, (size_t)B * n_first * k_top * 4, cudaMemcpyDeviceToHost, s));
+  B200W_CHECK_CUDA(cudaMemcpyAsync(h_lp, sp.out_logprobs, (size_t)B * n_first * k_top * 4, cudaMemcpyDeviceToHost, s));
   B200W_CHECK_CUDA(cudaStreamSynchronize(s));
 
   auto finish_stream = [&](StreamState& S) {
@@ -1124,9 +1139,10 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
 
   for (int b = 0; b < B; ++b) {
     StreamState& S = st[b];
-    for (int c = 0; c < k_top && (int)S.alive.size() < K; ++c) {
-      const int tok = h_ids[b * k_top + c];
-      const float lp = h_lp[b * k_top + c];
+    const int n_cand = sampling ? K : k_top;  // sampling: one draw per sample; search: the k_top best of the row
+    for (int c = 0; c < n_cand && (int)S.alive.size() < K; ++c) {
+      const int tok = sampling ? h_ids[c * B + b] : h_ids[b * k_top + c];
+      const float lp = sampling ? h_lp[c * B + b] : h_lp[b * k_top + c];
       if (tok == 0x7fffffff || !(lp > -INFINITY)) continue;
       if (tok == o.eot) {
         if ((int)S.finished.size() < max_cand) {
@@ -1151,7 +1167,8 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
   // it is live or not (idle rows decode a dummy token into a scratch slot), so that every step
   // issues the same launches on the same buffers and can be replayed as a CUDA graph.
   const int opts_hash = o.eot * 31 + o.timestamp_begin * 17 + o.max_initial_timestamp_index * 7 + k_top +
-                        (o.without_timestamps ? 1000003 : 0);
+                        (o.without_timestamps ? 1000003 : 0) +
+                        (sampling ? (int)(__builtin_bit_cast(unsigned, o.temperature) * 2654435761u + o.seed * 40503u) : 0);
   B200W_CHECK_CUDA(cudaMemsetAsync(e->tables[cur ^ 1].p, 0, (size_t)e->cfg.max_batch * e->cfg.max_beam * Tctx * 4, s));
   auto enqueue_step = [&](const PassMeta& m, size_t meta_bytes, int from) {
     B200W_CHECK_CUDA(cudaMemcpyAsync(e->meta.p, e->h_meta.p, meta_bytes, cudaMemcpyHostToDevice, s));
@@ -1191,7 +1208,7 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
           Hyp& h = S.alive[k];
           const int pos = S.P + step - 1;
           const int slot = b * e->slots_per_stream + S.P + (step - 1) * K + k;
-          hm.push(h.tokens.back(), pos, slot, row, pos + 1, b, sampling_state(h.tokens, o), h.table_row);
+          hm.push(h.tokens.back(), pos, slot, row, pos + 1, b, sampling_state(h.tokens, o, row), h.table_row);
           h.table_row = row;
           any = true;
         } else {  // idle row: one dummy token at position 0 in a scratch slot of its own
@@ -1265,6 +1282,29 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
       if (S.done) continue;
       const int na = (int)S.alive.size();
       const int r0 = b * K;
+      if (sampling) {  // every sample continues with its own draw
+        std::vector<Hyp> next;
+        for (int k = 0; k < na; ++k) {
+          const int tok = h_ids[r0 + k];
+          const float lp = h_lp[r0 + k];
+          Hyp& par = S.alive[k];
+          if (tok == 0x7fffffff || !(lp > -INFINITY) || tok == o.eot) {  // (no admissible token: the sample ends)
+            Finished f;
+            f.tokens = par.tokens;
+            f.cum = par.cum + (lp > -INFINITY ? (double)lp : 0.0);
+            f.score = norm_score(f.cum, (int)par.tokens.size(), o.length_penalty);
+            S.finished.push_back(std::move(f));
+            continue;
+          }
+          par.tokens.push_back(tok);
+          par.cum += (double)lp;
+          next.push_back(std::move(par));
+        }
+        S.alive.swap(next);
+        if (S.alive.empty()) { S.done = true; continue; }
+        if (step + 1 >= S.max_new) finish_stream(S);
+        continue;
+      }
       struct Cand { double score; int k, tok; float lp; };
       std::vector<Cand> cands;
       cands.reserve((size_t)na * k_top);

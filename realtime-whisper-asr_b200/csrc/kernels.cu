@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
 //    CTA the largest such value over its warps.  About k + a few dozen of the 51 866 elements pass.
 // Reductions have the shape of the streaming kernel's (same threads, same element-to-thread map, same trees), so
 // maxima, sums and therefore every log-probability are bit-identical to it.
+template <bool SAMPLING>
 __global__ void __launch_bounds__(SAMPLE_THREADS, 1) sample_row_kernel(const SampleParams p) {
   extern __shared__ __align__(16) float s_row[];  // [ceil(V / 4) * 4]
   __shared__ float s_red[32];
@@ -551,30 +552,108 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) sample_row_kernel(const Sam
   const float my_all = mx, my_ts = mx_ts;
   mx = block_max_1024(mx, s_red);  // (the barriers inside also publish the row)
   mx_text = block_max_1024(mx_text, s_red);
+  // sampling: the distribution is softmax(x / T); everything below works on y = (x - max) / T
+  const float inv_t = SAMPLING ? 1.0f / p.temperature : 1.0f;
   float sum_all = 0.f, sum_ts = 0.f;
   for (int i = tid; i < nv4; i += SAMPLE_THREADS) {
     const float4 x = s4[i];
     const int v = 4 * i;
-    const float e0 = __expf(x.x - mx), e1 = __expf(x.y - mx), e2 = __expf(x.z - mx), e3 = __expf(x.w - mx);
+    float e0, e1, e2, e3;
+    if (SAMPLING) {
+      e0 = __expf((x.x - mx) * inv_t); e1 = __expf((x.y - mx) * inv_t);
+      e2 = __expf((x.z - mx) * inv_t); e3 = __expf((x.w - mx) * inv_t);
+    } else {
+      e0 = __expf(x.x - mx); e1 = __expf(x.y - mx); e2 = __expf(x.z - mx); e3 = __expf(x.w - mx);
+    }
     sum_all += (e0 + e1) + (e2 + e3);
     if (v + 3 >= tb) sum_ts += (v >= tb ? e0 : 0.f) + (v + 1 >= tb ? e1 : 0.f) + (v + 2 >= tb ? e2 : 0.f) + e3;
   }
   for (int v = 4 * nv4 + tid; v < V; v += SAMPLE_THREADS) {
-    const float e = __expf(s_row[v] - mx);
+    const float e = __expf((s_row[v] - mx) * inv_t);
     sum_all += e;
     if (v >= tb) sum_ts += e;
   }
+  const float my_sum_all = sum_all, my_sum_ts = sum_ts;  // this thread's part (the sampler's inverse CDF)
   sum_all = block_sum_1024(sum_all, s_red);
   sum_ts = block_sum_1024(sum_ts, s_red);
   float lse = mx + logf(sum_all);
   int v_lo = 0;
   if (rules && sum_ts > 0.f) {
-    const float ts_logprob = mx + logf(sum_ts) - lse;
-    const float text_logprob = mx_text - lse;
+    const float ts_logprob = SAMPLING ? logf(sum_ts) - logf(sum_all) : mx + logf(sum_ts) - lse;
+    const float text_logprob = SAMPLING ? (mx_text - mx) * inv_t - logf(sum_all) : mx_text - lse;
     if (ts_logprob > text_logprob) {
       v_lo = tb;
       lse = mx + logf(sum_ts);
     }
+  }
+
+  if (SAMPLING) {
+    // inverse CDF in thread-major order (thread, then its elements in the order of the passes above): the thread whose
+    // interval of the running sum contains u * total walks its elements again
+    __shared__ float s_scan[SAMPLE_WARPS];
+    __shared__ int s_pick[2];
+    const float mine = v_lo == 0 ? my_sum_all : my_sum_ts, total = v_lo == 0 ? sum_all : sum_ts;
+    float incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t2 = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t2;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    if (tid == 0) { s_pick[0] = 0x7fffffff; s_pick[1] = -1; }
+    __syncthreads();
+    float base = 0.f;
+    for (int w = 0; w < warp; ++w) base += s_scan[w];
+    const float hi = base + incl, lo = hi - mine;
+    // u in [0, 1): splitmix64 of (seed, sample stream, draw index)
+    unsigned long long z = ((unsigned long long)p.seed << 32) ^ ((unsigned long long)(unsigned)st.w << 20) ^ (unsigned)st.z;
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+    const float target = u * total;
+    auto walk = [&](float from, bool take_last) {  // this thread's elements; returns through s_pick
+      float run = from;
+      int last = -1;
+      for (int i = tid; i < nv4; i += SAMPLE_THREADS) {
+        const float4 x = s4[i];
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int v = 4 * i + c;
+          if (v >= v_lo && xs[c] > -INFINITY) {
+            run += __expf((xs[c] - mx) * inv_t);
+            last = v;
+            if (!take_last && run > target) return v;
+          }
+        }
+      }
+      for (int v = 4 * nv4 + tid; v < V; v += SAMPLE_THREADS) {
+        const float x = s_row[v];
+        if (v >= v_lo && x > -INFINITY) {
+          run += __expf((x - mx) * inv_t);
+          last = v;
+          if (!take_last && run > target) return v;
+        }
+      }
+      return last;
+    };
+    int pick = -1;
+    if (mine > 0.f && target >= lo && target < hi) pick = walk(lo, false);
+    if (pick >= 0) atomicMin(&s_pick[0], pick);                 // (rounding: more than one interval may claim it)
+    if (mine > 0.f) atomicMax(&s_pick[1], tid);                  // fallback: the last thread holding any mass
+    __syncthreads();
+    if (s_pick[0] == 0x7fffffff && tid == s_pick[1]) {           // target fell on the rounding gap at the very end
+      const int v = walk(0.f, true);
+      if (v >= 0) s_pick[0] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int v = s_pick[0];
+      p.out_ids[row] = v;
+      p.out_logprobs[row] = v == 0x7fffffff ? -INFINITY : (s_row[v] - mx) * inv_t - logf(total);
+    }
+    return;
   }
 
   const int k = p.k;
@@ -673,9 +752,14 @@ void sample_topk(const SampleParams& p, int rows, cudaStream_t stream, bool stre
   B200W_REQUIRE(p.k >= 1 && p.k <= MAX_TOPK, "top-k out of range");
   const size_t row_bytes = (size_t)((p.n_vocab + 3) / 4) * 16;
   static const bool streaming_only = getenv("B200W_SAMPLE_STREAMING") != nullptr;
-  if (!streaming && !streaming_only && row_bytes <= 220 * 1024) {
-    ensure_dynamic_smem(sample_row_kernel, row_bytes);
-    launch_pdl(sample_row_kernel, dim3(rows), dim3(SAMPLE_THREADS), row_bytes, stream, p);
+  if (p.temperature > 0.f) {
+    B200W_REQUIRE(p.k == 1, "sampling draws one token per row");
+    B200W_REQUIRE(row_bytes <= 220 * 1024, "sampling needs the row in shared memory (vocabulary too large)");
+    ensure_dynamic_smem(sample_row_kernel<true>, row_bytes);
+    launch_pdl(sample_row_kernel<true>, dim3(rows), dim3(SAMPLE_THREADS), row_bytes, stream, p);
+  } else if (!streaming && !streaming_only && row_bytes <= 220 * 1024) {
+    ensure_dynamic_smem(sample_row_kernel<false>, row_bytes);
+    launch_pdl(sample_row_kernel<false>, dim3(rows), dim3(SAMPLE_THREADS), row_bytes, stream, p);
   } else {
     launch_pdl(sample_kernel, dim3(rows), dim3(SAMPLE_THREADS), 0, stream, p);
   }

@@ -42,6 +42,11 @@ struct SampleParams {
   int k;
   int* out_ids;         // [rows][k]
   float* out_logprobs;  // [rows][k]
+  // temperature > 0: instead of the k best, ONE token per row drawn from softmax(masked logits / temperature)
+  // (k must be 1); the draw of a row is a pure function of (seed, state[row].z = draw index, state[row].w = sample
+  // stream), the log-probability returned is the token's under the tempered distribution
+  float temperature = 0.f;
+  unsigned seed = 0;
 };
 void sample_topk(const SampleParams& p, int rows, cudaStream_t stream, bool streaming = false);
 

@@ -31,6 +31,9 @@ class DecodeOptions:
     timestamp_begin: int = 50364
     suppress_ids: Sequence[int] = field(default_factory=list)
     blank_ids: Sequence[int] = field(default_factory=list)
+    temperature: float = 0.0   # > 0: best_of independent samples instead of greedy / beam search
+    best_of: int = 1
+    seed: int = 0
 
 
 @dataclass
@@ -118,7 +121,8 @@ class WhisperEngine:
         c = _lib.DecodeOpts(o.beam_size, o.patience, o.length_penalty, o.max_new_tokens,
                             int(o.suppress_blank), int(o.without_timestamps), o.max_initial_timestamp_index,
                             o.eot, o.sot, o.no_speech, o.no_timestamps, o.timestamp_begin,
-                            _p_i32(sup), len(sup), _p_i32(blk), len(blk))
+                            _p_i32(sup), len(sup), _p_i32(blk), len(blk),
+                            float(o.temperature), int(o.best_of), int(o.seed) & 0xFFFFFFFF)
         return c, (sup, blk)
 
     def decode(self, cross_kv: torch.Tensor, prompts: Sequence[Sequence[int]], opts: DecodeOptions) -> List[DecodeResult]:

@@ -349,6 +349,7 @@ class B200WhisperModel:
             self.lane_streams = [torch.cuda.Stream(self.device) for _ in range(self.n_lanes)] if self.n_lanes > 1 else []
         self.engine = self.engines[0]
         self._pool = None
+        self._sample_seed = 0  # advances per decode call: draws differ between calls, runs are reproducible
         self.max_batch = max_batch
         self.max_beam = max_beam
         self.last_timings = {}
@@ -409,13 +410,12 @@ class B200WhisperModel:
             raise NotImplementedError("vad_filter: the VAD gate sits in the caller (Silero in the reference)")
         if repetition_penalty != 1 or no_repeat_ngram_size != 0:
             raise NotImplementedError("repetition_penalty / no_repeat_ngram_size are not implemented")
-        temps = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
-        if temps[0] != 0:
-            # the reference passes 0.0 (一键实时识别麦克风.py:1121-1124); its unused adaptive hook may ask for 0.1
-            # (speech_rate_audio_processor.py:214-218).  Sampling is not implemented: decode deterministically.
-            self._warn_once("temperature", f"temperature={temps[0]}: sampling is not implemented, decoding with "
-                                           "temperature 0 (beam search / greedy)")
+        temps = [float(temperature)] if isinstance(temperature, (int, float)) else [float(t) for t in temperature]
+        if not temps:
             temps = [0.0]
+        if best_of > self.max_beam and any(t > 0 for t in temps):
+            self._warn_once("best_of", f"best_of {best_of} exceeds this engine's max_beam {self.max_beam}: clamped")
+            best_of = self.max_beam
         if beam_size > self.max_beam:
             self._warn_once("beam", f"beam_size {beam_size} exceeds this engine's max_beam {self.max_beam}: clamped "
                                     "(build the model with max_beam=... to raise it, at most 8)")
@@ -436,7 +436,7 @@ class B200WhisperModel:
         options = TranscriptionOptions(beam_size, best_of, patience, length_penalty, repetition_penalty,
                                        no_repeat_ngram_size, log_prob_threshold, no_speech_threshold,
                                        compression_ratio_threshold, condition_on_previous_text,
-                                       prompt_reset_on_temperature, temps[:1], None, prefix, suppress_blank,
+                                       prompt_reset_on_temperature, temps, None, prefix, suppress_blank,
                                        list(suppress_tokens) if suppress_tokens is not None else None,
                                        without_timestamps, max_initial_timestamp, word_timestamps,
                                        prepend_punctuations, append_punctuations, max_new_tokens)
@@ -502,7 +502,8 @@ class B200WhisperModel:
                 out.append((allp[0][0], allp[0][1], allp))
         return out
 
-    def _decode_options(self, tk: Tokenizer, o: TranscriptionOptions) -> DecodeOptions:
+    def _decode_options(self, tk: Tokenizer, o: TranscriptionOptions, temperature: float = 0.0,
+                        seed: int = 0) -> DecodeOptions:
         """Decoder options of a batch.  The suppress sets depend on the vocabulary, the model's special-token layout
         and the call's ``suppress_tokens`` -- never on a stream's language or task -- so one set serves the batch.
         A CTranslate2 config.json's ``suppress_ids`` / ``suppress_ids_begin`` take the place of the lists derived
@@ -522,7 +523,8 @@ class B200WhisperModel:
             max_initial_timestamp_index=int(round(o.max_initial_timestamp / TIME_PRECISION)),
             eot=tk.eot, sot=tk.sot, no_speech=tk.no_speech, no_timestamps=tk.no_timestamps,
             timestamp_begin=tk.timestamp_begin,
-            suppress_ids=suppress, blank_ids=blank)
+            suppress_ids=suppress, blank_ids=blank,
+            temperature=temperature, best_of=max(1, min(o.best_of, self.max_beam)), seed=seed)
 
     def _run_streams(self, mel: frontend.MelBatch, streams: List[_Stream], max_rounds: Optional[int] = None) -> None:
         """Rounds of (pack windows -> encode -> cross K/V -> decode -> align) over the live streams.
@@ -575,6 +577,54 @@ class B200WhisperModel:
         self.last_timings[name] = self.last_timings.get(name, 0.0) + (now - t0)
         return now
 
+    def _decode_with_fallback(self, engine: WhisperEngine, ckv: torch.Tensor, batch: List["_Stream"],
+                              o: TranscriptionOptions):
+        """faster-whisper's generate_with_fallback over a batch: decode every chunk at the first temperature; the
+        chunks whose result is too repetitive (compression ratio) or too unlikely (average log-probability) -- and is
+        not silence -- are decoded again at the next temperature (sampling, best_of samples), and so on; a chunk that
+        fails everywhere keeps its most likely result among those below the compression threshold (or among all)."""
+        n = len(batch)
+        final: List = [None] * n
+        temp_of = [o.temperatures[0]] * n
+        history: List[List] = [[] for _ in range(n)]  # per chunk: (result, avg_logprob, compression_ratio, temperature)
+        pending = list(range(n))
+        for ti, temp in enumerate(o.temperatures):
+            if not pending:
+                break
+            if len(pending) == n:
+                sub_ckv, prompts = ckv, [s.prompt for s in batch]
+            else:
+                idx = torch.tensor(pending, dtype=torch.long, device=ckv.device)
+                sub_ckv, prompts = ckv.index_select(0, idx), [batch[i].prompt for i in pending]
+            self._sample_seed += 1
+            res = engine.decode(sub_ckv, prompts, self._decode_options(self.tokenizer("en"), o, temp, self._sample_seed))
+            still = []
+            for i, r in zip(pending, res):
+                tk = batch[i].tokenizer
+                avg_logprob = r.sum_logprob / (len(r.tokens) + 1)
+                text = tk.decode(r.tokens).strip()
+                cr = get_compression_ratio(text) if text else 0.0
+                history[i].append((r, avg_logprob, cr, temp))
+                needs_fallback = False
+                if o.compression_ratio_threshold is not None and cr > o.compression_ratio_threshold:
+                    needs_fallback = True
+                if o.log_prob_threshold is not None and avg_logprob < o.log_prob_threshold:
+                    needs_fallback = True
+                if (o.no_speech_threshold is not None and r.no_speech_prob > o.no_speech_threshold
+                        and o.log_prob_threshold is not None and avg_logprob < o.log_prob_threshold):
+                    needs_fallback = False  # silence
+                if needs_fallback and ti + 1 < len(o.temperatures):
+                    still.append(i)
+                elif needs_fallback:  # every temperature failed
+                    ok = [h for h in history[i]
+                          if o.compression_ratio_threshold is None or h[2] <= o.compression_ratio_threshold]
+                    best = max(ok or history[i], key=lambda h: h[1])
+                    final[i], temp_of[i] = best[0], best[3]
+                else:
+                    final[i], temp_of[i] = r, temp
+            pending = still
+        return final, temp_of
+
     def _round(self, mel: frontend.MelBatch, batch: List[_Stream], engine: WhisperEngine) -> None:
         import time as _t
         o = batch[0].options
@@ -589,7 +639,7 @@ class B200WhisperModel:
         ckv = engine.cross_kv(enc)
         t = self._phase("cross_kv", t)
         # one set of decoder options per batch: they do not depend on a stream's language or task (see there)
-        results = engine.decode(ckv, [s.prompt for s in batch], self._decode_options(self.tokenizer("en"), o))
+        results, used_temp = self._decode_with_fallback(engine, ckv, batch, o)
         t = self._phase("decode", t)
         to_align = []  # (stream, subsegments, text_tokens, row in ckv)
         per_stream = []
@@ -611,7 +661,8 @@ class B200WhisperModel:
             segment_duration = s.segment_size * HOP / SAMPLE_RATE
             subs, new_seek, single_ending = split_segments_by_timestamps(tk, tokens, s.time_offset, s.segment_size,
                                                                         segment_duration, s.seek)
-            per_stream.append((s, subs, new_seek, single_ending, avg_logprob, compression_ratio, res.no_speech_prob))
+            per_stream.append((s, subs, new_seek, single_ending, avg_logprob, compression_ratio, res.no_speech_prob,
+                               used_temp[row]))
             if o.word_timestamps:
                 text_tokens = [t for sub in subs for t in sub["tokens"] if t < tk.eot]
                 to_align.append((len(per_stream) - 1, row, text_tokens))
@@ -621,7 +672,7 @@ class B200WhisperModel:
         for entry in per_stream:
             if entry is None:
                 continue
-            s, subs, new_seek, single_ending, avg_logprob, compression_ratio, nsp = entry
+            s, subs, new_seek, single_ending, avg_logprob, compression_ratio, nsp, temp = entry
             tk = s.tokenizer
             if o.word_timestamps and not single_ending:
                 last_word_end = None
@@ -641,8 +692,9 @@ class B200WhisperModel:
                 s.idx += 1
                 words = [Word(**w) for w in sub["words"]] if o.word_timestamps else None
                 s.segments.append(Segment(s.idx, sub["seek"], sub["start"], sub["end"], text, tokens, avg_logprob,
-                                          compression_ratio, nsp, words, 0.0))
-            if not o.condition_on_previous_text:
+                                          compression_ratio, nsp, words, temp))
+            # (faster-whisper: text produced at a high temperature is not fed back as a prompt)
+            if not o.condition_on_previous_text or temp > o.prompt_reset_on_temperature:
                 s.prompt_reset_since = len(s.all_tokens)
 
     def _align_batch(self, engine, ckv, batch, per_stream, to_align, o: TranscriptionOptions) -> None:

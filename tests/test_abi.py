@@ -26,7 +26,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_load_and_version():
     lib = _lib.load()
-    assert lib.b200w_abi_version() == 2
+    assert lib.b200w_abi_version() == 3
     assert lib.b200w_launch_count() >= 0
     assert lib.b200w_last_error() is not None
 

@@ -47,6 +47,37 @@ def test_backend_contract(model):
         asr.transcribe(audio)
 
 
+def test_temperature_sampling_and_fallback(model):
+    """faster-whisper's temperature semantics (the reference forwards `temperature`, asr_components.py:283, and its
+    adaptive hook may raise it, speech_rate_audio_processor.py:214-218): a positive temperature samples best_of
+    hypotheses, a tuple is a fallback ladder driven by the compression-ratio / log-probability thresholds."""
+    audio = speech_like(5, 10.0)
+    kw = dict(language="en", beam_size=5, word_timestamps=True, condition_on_previous_text=False)
+    greedy, _ = model.transcribe(audio, temperature=0.0, **kw)
+    greedy = list(greedy)
+    assert greedy and all(s.temperature == 0.0 for s in greedy)
+    # sampling: well-formed (timestamp grammar, ordered words), flagged with its temperature
+    a, _ = model.transcribe(audio, temperature=0.8, best_of=3, **kw)
+    a = list(a)
+    assert a and all(s.temperature == 0.8 for s in a)
+    for s in a:
+        assert s.end >= s.start and all(w.end >= w.start for w in s.words)
+    # a ladder whose first rung cannot pass (log-probability threshold above 0) falls through to the last rung; every
+    # rung fails, so each chunk keeps the rung with the best average log-probability
+    b, info = model.transcribe(audio, temperature=(0.0, 0.5), best_of=2, log_prob_threshold=1.0,
+                               no_speech_threshold=None, **kw)
+    b = list(b)
+    assert b and all(s.temperature in (0.0, 0.5) for s in b)
+    assert info.transcription_options.temperatures == [0.0, 0.5]
+    # thresholds that always pass: the ladder stops at the first rung and equals plain temperature-0 decoding
+    c, _ = model.transcribe(audio, temperature=(0.0, 0.5, 1.0), log_prob_threshold=None,
+                            compression_ratio_threshold=None, **kw)
+    assert _tokens(list(c)) == _tokens(greedy)
+    # the ASR backend forwards the keyword unchanged
+    asr = B200WhisperASR("en", model=model, transcribe_kwargs={"beam_size": 5, "temperature": 0.1, "best_of": 2})
+    assert asr.transcribe(audio, init_prompt="")
+
+
 def test_model_dir_formats_and_missing_checkpoint(cuda_device, tmp_path):
     """the reference constructs its backend from a CTranslate2 model directory or a size name
     (/root/reference/asr_components.py:232-265).  A CT2 model.bin directory and a Hugging Face safetensors directory
@@ -81,7 +112,7 @@ def test_model_dir_formats_and_missing_checkpoint(cuda_device, tmp_path):
         segs, info = m.transcribe(audio, language="en", beam_size=1, word_timestamps=True)  # HF vocabulary path runs
         assert info.language == "en" and isinstance(list(segs), list)
         if "download_root" in kwargs:  # CT2 config.json lists replace the vocabulary-derived suppress sets
-            o = m._decode_options(m.tokenizer("en"), m.transcribe_batch([audio], languages=["en"], beam_size=1)[0][1].transcription_options)
+            o = m._decode_options(m.tokenizer("en"), m.transcribe_batch([audio], languages=["en"], beam_size=1, temperature=0.0)[0][1].transcription_options)
             assert {1, 2, 7} <= set(o.suppress_ids) and list(o.blank_ids) == [220, 50257]
         m.engine.close()
     # through the reference-shaped constructor too: modelsize + cache_dir (MAIN:1125-1134)
@@ -98,17 +129,19 @@ def test_model_dir_formats_and_missing_checkpoint(cuda_device, tmp_path):
 def test_options_degrade_instead_of_raising(model):
     """/root/reference/asr_components.py:270-288 forwards whatever beam_size / temperature its config or adaptive
     hook holds (speech_rate_audio_processor.py:214-218: beam up to 10, temperature 0.1).  Neither may throw in the
-    middle of a stream: the beam is clamped to the engine's, a sampling temperature decodes deterministically;
+    middle of a stream: the beam (and best_of) is clamped to the engine's, a positive temperature samples;
     token-id initial prompts (faster-whisper's Iterable[int] form) are accepted."""
     audio = speech_like(13, 5.0)
     base = [s.tokens for s in model.transcribe(audio, language="en", beam_size=5, temperature=0.0)[0]]
-    assert [s.tokens for s in model.transcribe(audio, language="en", beam_size=10, temperature=0.1)[0]] == base
+    assert [s.tokens for s in model.transcribe(audio, language="en", beam_size=10, temperature=0.0)[0]] == base
+    assert list(model.transcribe(audio, language="en", beam_size=10, best_of=10, temperature=0.1)[0])
     tk = model.tokenizer("en")
-    a = [s.tokens for s in model.transcribe(audio, language="en", beam_size=1, initial_prompt="hello there")[0]]
-    b = [s.tokens for s in model.transcribe(audio, language="en", beam_size=1,
+    a = [s.tokens for s in model.transcribe(audio, language="en", beam_size=1, temperature=0.0,
+                                            initial_prompt="hello there")[0]]
+    b = [s.tokens for s in model.transcribe(audio, language="en", beam_size=1, temperature=0.0,
                                             initial_prompt=tk.encode(" hello there"))[0]]
     assert a == b
-    two = model.transcribe_batch([audio, audio], languages=["en", "en"], beam_size=1,
+    two = model.transcribe_batch([audio, audio], languages=["en", "en"], beam_size=1, temperature=0.0,
                                  initial_prompts=["hello there", None])
     assert [s.tokens for s in two[0][0]] == a
 

@@ -159,7 +159,7 @@ def test_sample_topk(lib, cuda_device, V, k, rows):
         lps = torch.zeros(rows, k, dtype=torch.float32, device=cuda_device)
         work = dl.clone()  # the streaming kernel masks its input in place
         _lib.check(lib.b200w_sample_topk(work.data_ptr(), rows, ld, V, dm.data_ptr(), ds.data_ptr(), eot, no_ts, tb, 50,
-                                         k, ids.data_ptr(), lps.data_ptr(), streaming,
+                                         k, ids.data_ptr(), lps.data_ptr(), streaming, 0.0, 0,
                                          torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         res.append((ids.cpu().numpy(), lps.cpu().numpy()))
@@ -171,3 +171,56 @@ def test_sample_topk(lib, cuda_device, V, k, rows):
     fin = np.isfinite(ref_lp)
     assert np.array_equal(fin, np.isfinite(res[0][1]))
     assert np.abs(res[0][1][fin] - ref_lp[fin]).max() <= 2e-5
+
+
+def test_sample_temperature(lib, cuda_device):
+    """Sampling mode: many draws from one row (different draw indices) follow softmax(masked logits / T); the returned
+    log-probability is the token's under that distribution; barred tokens are never drawn; draws are reproducible."""
+    g = torch.Generator(device="cpu").manual_seed(11)
+    V, T, rows = 2048 + 3, 0.7, 8192
+    ld = (V + 7) // 8 * 8
+    tb = V - 101
+    eot, no_ts = tb - 10, tb - 1
+    row = torch.randn(ld, generator=g) * 2.0
+    mask = (torch.rand(V, generator=g) < 0.1).to(torch.uint8)
+    logits = row.expand(rows, ld).contiguous()
+    state = torch.zeros(rows, 4, dtype=torch.int32)
+    state[:, 2] = torch.arange(rows, dtype=torch.int32)  # draw index
+    state[:, 3] = 5
+    dl, dm, ds = logits.to(cuda_device), mask.to(cuda_device), state.to(cuda_device)
+
+    def draw(seed):
+        ids = torch.zeros(rows, dtype=torch.int32, device=cuda_device)
+        lps = torch.zeros(rows, dtype=torch.float32, device=cuda_device)
+        _lib.check(lib.b200w_sample_topk(dl.data_ptr(), rows, ld, V, dm.data_ptr(), ds.data_ptr(), eot, no_ts, tb, 50, 1,
+                                         ids.data_ptr(), lps.data_ptr(), 0, T, seed,
+                                         torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return ids.cpu().numpy(), lps.cpu().numpy()
+
+    ids, lps = draw(3)
+    ids2, _ = draw(3)
+    ids3, _ = draw(4)
+    assert np.array_equal(ids, ids2) and not np.array_equal(ids, ids3)
+    x = row[:V].double().clone()
+    x[mask.bool()] = -np.inf
+    ref_lp = torch.log_softmax(x / T, -1).numpy()
+    assert np.all(np.isfinite(ref_lp[ids])), "a barred token was drawn"
+    assert np.abs(lps - ref_lp[ids]).max() <= 2e-4
+    # empirical frequencies of the 12 likeliest tokens vs their probabilities (binomial 5 sigma)
+    p = np.exp(ref_lp)
+    for tok in np.argsort(-p)[:12]:
+        f = np.mean(ids == tok)
+        assert abs(f - p[tok]) <= 5 * np.sqrt(p[tok] * (1 - p[tok]) / rows) + 1e-4, (tok, f, p[tok])
+    # with the timestamp rules on and the timestamps carrying most of the mass, only timestamps are drawn
+    logits2 = logits.clone()
+    logits2[:, tb:V] += 8.0
+    state2 = state.clone()
+    state2[:, 0] = SF_RULES
+    ids_t = torch.zeros(rows, dtype=torch.int32, device=cuda_device)
+    lps_t = torch.zeros(rows, dtype=torch.float32, device=cuda_device)
+    _lib.check(lib.b200w_sample_topk(logits2.to(cuda_device).data_ptr(), rows, ld, V, dm.data_ptr(),
+                                     state2.to(cuda_device).data_ptr(), eot, no_ts, tb, 50, 1, ids_t.data_ptr(),
+                                     lps_t.data_ptr(), 0, T, 3, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert (ids_t.cpu().numpy() >= tb).all()

@@ -83,5 +83,5 @@ lps = torch.zeros(rows, k, device=dev)
 for streaming in (0, 1):
     t = time_loop(lambda: _lib.check(lib.b200w_sample_topk(logits.data_ptr(), rows, ld, V, mask.data_ptr(), state.data_ptr(),
                                                            50257, 50363, 50365, 50, k, ids.data_ptr(), lps.data_ptr(),
-                                                           streaming, st)))
+                                                           streaming, 0.0, 0, st)))
     print(f"sample_topk {'streaming' if streaming else 'on-chip row'}: {t:7.2f} us ({rows} rows x {V})")
