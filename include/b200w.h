@@ -154,8 +154,8 @@ int b200w_cross_attention_flash(const void* cross_kv_dev, int n_streams, int n_l
 
 /* Decode-step self-attention (csrc/attention.cu, qkv_attn_kernel): split-K partial sums of the fused QKV
  * projection -> bias, bf16 -> the row's new key / value into the paged cache -> attention over the row's history
- * (through its page-table row) plus its own position.  rows_per_group consecutive rows (the beams of one stream,
- * <= 8) are handled by one CTA per head.
+ * (through its page-table row) plus its own position; one warp per (row, head), n_heads % 4 == 0.  rows_per_group:
+ * how many consecutive rows belong to one stream (a hint, unused by the shipped kernel).
  *   partial_dev fp32 [n_splits][rows][3d]   bias_dev fp32 [3d]   slot_dev int32 [rows] slot of the row's own token
  *   kpool_dev / vpool_dev bf16 [slots][d]   table_dev int32 [table rows][table_stride] position -> slot
  *   trow_dev int32 [rows] page-table row    kvlen_dev int32 [rows] visible keys INCLUDING the row's own position

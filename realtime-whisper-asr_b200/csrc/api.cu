@@ -221,7 +221,7 @@ int b200w_step_self_attention(const float* partial_dev, int n_splits, const floa
   qa.kpool = static_cast<bf16*>(kpool_dev); qa.vpool = static_cast<bf16*>(vpool_dev);
   qa.table = table_dev; qa.table_stride = table_stride; qa.trow = trow_dev; qa.kvlen = kvlen_dev;
   qa.out = static_cast<bf16*>(out_dev); qa.out_stride = d; qa.scale = 0.125f; qa.max_len = max_len;
-  qa.rows_per_cta = rows_per_group;
+  (void)rows_per_group;  // (grouping hint of an experimental kernel: the shipped kernel works row by row)
   qkv_attention(qa, rows, n_heads, static_cast<cudaStream_t>(stream));
   B200W_API_END
 }

@@ -782,353 +782,140 @@ __global__ void __launch_bounds__(NW * 32) dec_attn_kernel(const DecAttnParams p
   *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
 }
 
-// Decode steps: the QKV projection arrives as split-K partial sums.  This kernel reduces the slabs (bias, bf16
-// rounding: the same arithmetic as split_finalize), writes the new keys / values into the cache, and attends: a
-// row's history comes from the cache through its page table, its own position (the last one) from shared memory.
-// One launch instead of reduction + attention, and q never goes through global memory.
-//
-// One CTA = one head of the G consecutive rows of one stream (its beams).  The kernel is latency-bound (a history
-// of ~100 positions is 25 KB per (row, head)), so it is organised as a short chain of phases in each of which
-// EVERY load of the CTA is in flight at once (explicit register batches: the compiler does not batch loads across
-// iterations of a loop with stores in it), instead of one warp walking a row with a round trip per 32 positions:
-//   A  row metadata + all slab reads        -> q, k, v in shared memory, k / v into the cache
-//   B  the rows' page tables                -> shared memory
-//   C  common prefix of the page tables (beams share their prompt and the older part of their history: a fork
-//      copies page-table rows, never K/V bytes)
-//   D  scores: "items" = one shared position for all rows, or one (row, position) pair of the unshared tail (the
-//      row's own position included); one THREAD per item: it loads the 128-byte key row once and multiplies it
-//      with every row's query (broadcast reads of shared memory) -- no shuffles, ~1.3 instructions per FMA
-//   E  softmax, one warp per row
-//   F  P.V: positions dealt to the warps, a lane owns 2 of the 64 dims of every row; the value row of a shared
-//      position is loaded once for all rows; 8 rows in flight per warp; partial sums reduced in shared memory.
-// (Two earlier layouts -- 4 lanes per (row, position), and 8 lanes per item with shuffle reductions -- were
-// instruction-issue bound: ncu counted 22.5 M warp instructions per launch at the bench shape.)
-static constexpr int QG_MAX_ROWS = 8;
-
-template <int GM>
-__device__ __forceinline__ int hist_r_dyn(const int (&hist_r)[GM], int g) {
-  int v = -1;
-#pragma unroll
-  for (int j = 0; j < GM; ++j)
-    if (j == g) v = hist_r[j];
-  return v;
-}
-
-template <int NT, int GM, int MIN_CTAS>
-__global__ void __launch_bounds__(NT, MIN_CTAS) qkv_attn_kernel(const QkvAttnParams p) {
-  constexpr int NW = NT / 32, UB = 8;
-  extern __shared__ float s_dyn[];  // [G][max_len] page table (int) | [G][max_len] scores / probabilities
-  __shared__ __align__(16) float s_q[GM][HD], s_k[GM][HD], s_v[GM][HD];
-  __shared__ __align__(16) float s_acc[NW][GM][HD];
-  __shared__ int s_hist[QG_MAX_ROWS], s_trow[QG_MAX_ROWS];
-  __shared__ float s_inv[QG_MAX_ROWS];
-  __shared__ int s_common;
+// (Round 2 tried to regroup this kernel per (stream, head) -- the beams of a stream in one CTA, key / value rows of
+// the shared history loaded once for all beams, scores by one thread per (beam, position), every load of a phase in
+// flight at once.  It passed the block tests and lost: 30.4 us per launch against 25.3 us in the ncu launch list of
+// a full bench step and 4.33 ms against 4.10 ms per decode step in an A/B on one box (tools/gpu_ab.sh) -- ~11 M
+// warp instructions per launch, issue-bound.  This kernel, one warp per (row, head), stays.)
+// Decode steps: the QKV projection arrives as split-K partial sums.  This kernel reduces the slabs of ITS
+// row and head group (bias, bf16 rounding: the same arithmetic as split_finalize), writes the new key /
+// value into the cache, and attends: the row's history comes from the cache through the page table, its
+// own position (the last one) from shared memory.  One launch instead of reduction + attention, and q
+// never goes through global memory.  A row only needs its own new key / value, so CTAs are independent.
+__global__ void __launch_bounds__(128) qkv_attn_kernel(const QkvAttnParams p) {
+  extern __shared__ float s_dyn[];  // [max_len] table (int) | [4][max_len] scores
+  __shared__ float s_q[256], s_k[256], s_v[256];
   pdl_trigger();
-  const int h = blockIdx.y;
+  const int qi = blockIdx.x, hg = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int G = p.rows_per_cta;  // <= GM
-  const int row0 = blockIdx.x * G;
-  const int d = p.d, N = 3 * d, ML = p.max_len;
-  const int n_live = min(G, p.n_rows - row0);  // rows of this CTA that exist
-  int* s_tab = reinterpret_cast<int*>(s_dyn);
-  float* sc = s_dyn + G * ML;
+  const int c = hg * 256 + 2 * tid;  // this thread's two columns inside each of the q / k / v sections
+  const int d = p.d, N = 3 * d;
+  float2 bq = __ldg(reinterpret_cast<const float2*>(p.bias + c));
+  float2 bk = __ldg(reinterpret_cast<const float2*>(p.bias + d + c));
+  float2 bv = __ldg(reinterpret_cast<const float2*>(p.bias + 2 * d + c));
   pdl_wait();
-
-  // ---- A: metadata; slabs -> q, k, v of this head for every row
-  if (tid < QG_MAX_ROWS) {
-    const bool ok = tid < n_live;
-    s_hist[tid] = ok ? p.kvlen[row0 + tid] - 1 : -1;  // positions [0, hist) come from the cache, hist is the own token
-    s_trow[tid] = ok ? p.trow[row0 + tid] : 0;
+  {
+    const float* pp = p.partial + (long long)qi * N + c;
+#pragma unroll 4
+    for (int s2 = 0; s2 < p.n_splits; ++s2) {
+      const float2 a = *reinterpret_cast<const float2*>(pp + s2 * p.split_stride);
+      const float2 b = *reinterpret_cast<const float2*>(pp + s2 * p.split_stride + d);
+      const float2 e = *reinterpret_cast<const float2*>(pp + s2 * p.split_stride + 2 * d);
+      bq.x += a.x; bq.y += a.y; bk.x += b.x; bk.y += b.y; bv.x += e.x; bv.y += e.y;
+    }
+  }
+  const __nv_bfloat162 q2 = __floats2bfloat162_rn(bq.x, bq.y), k2 = __floats2bfloat162_rn(bk.x, bk.y),
+                       v2 = __floats2bfloat162_rn(bv.x, bv.y);
+  const long long slot = p.slot[qi];
+  *reinterpret_cast<__nv_bfloat162*>(p.kpool + slot * d + c) = k2;
+  *reinterpret_cast<__nv_bfloat162*>(p.vpool + slot * d + c) = v2;
+  {
+    const float2 qf = __bfloat1622float2(q2), kf = __bfloat1622float2(k2), vf = __bfloat1622float2(v2);
+    s_q[2 * tid] = qf.x * p.scale; s_q[2 * tid + 1] = qf.y * p.scale;
+    s_k[2 * tid] = kf.x; s_k[2 * tid + 1] = kf.y;
+    s_v[2 * tid] = vf.x; s_v[2 * tid + 1] = vf.y;
+  }
+  int* s_tab = reinterpret_cast<int*>(s_dyn);
+  float* sc = s_dyn + p.max_len + warp * p.max_len;
+  const int len = p.kvlen[qi];
+  const int hist = len - 1;  // positions [0, hist) come from the cache, position hist is this row's own token
+  const int tr = p.trow[qi];
+  const int h = hg * 4 + warp;
+  const bf16* kb = p.kpool + h * HD;
+  const bf16* vb = p.vpool + h * HD;
+  {
+    const int* tab = p.table + (long long)tr * p.table_stride;
+    for (int i = tid; i < hist; i += 128) s_tab[i] = tab[i];
+  }
+  __syncthreads();
+  float q[HD];
+#pragma unroll
+  for (int i = 0; i < HD; ++i) q[i] = s_q[warp * HD + i];
+  float mx = -INFINITY;
+  for (int i = lane; i < hist; i += 32) {
+    const long long roff = (long long)s_tab[i] * d;
+    const bf16* kp = kb + roff;
+    uint4 kr[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) kr[cc] = __ldg(reinterpret_cast<const uint4*>(kp) + cc);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + roff));
+    float acc = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&kr[cc]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(u2[t]);
+        acc = fmaf(q[8 * cc + 2 * t], f.x, acc);
+        acc = fmaf(q[8 * cc + 2 * t + 1], f.y, acc);
+      }
+    }
+    sc[i] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  float own = 0.f;  // score of the row's own position (every lane computes it: smem broadcast reads)
+#pragma unroll
+  for (int i = 0; i < HD; ++i) own = fmaf(q[i], s_k[warp * HD + i], own);
+  mx = fmaxf(mx, own);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int i = lane; i < hist; i += 32) {
+    const float e = __expf(sc[i] - mx);
+    sc[i] = e;
+    sum += e;
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float p_own = __expf(own - mx);
+  sum += p_own;
+  const float inv = 1.0f / sum;
+  __syncwarp();
+  float2 acc = make_float2(p_own * s_v[warp * HD + 2 * lane], p_own * s_v[warp * HD + 2 * lane + 1]);
+  const bf16* vl = vb + 2 * lane;
+  int i = 0;
+  for (; i + 16 <= hist; i += 16) {
+    __nv_bfloat162 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)s_tab[i + u] * d);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const float pw = sc[i + u];
+      const float2 f = __bfloat1622float2(v[u]);
+      acc.x = fmaf(pw, f.x, acc.x);
+      acc.y = fmaf(pw, f.y, acc.y);
+    }
   }
   {
-    constexpr int TASKS = (GM * 96 + NT - 1) / NT;  // task = (row, q|k|v, column pair)
-    float2 acc[TASKS];
-    int slot[TASKS];
-    const float* src[TASKS];
+    __nv_bfloat162 v[16];
 #pragma unroll
-    for (int j = 0; j < TASKS; ++j) {
-      const int t = tid + j * NT;
-      const bool ok = t < n_live * 96;
-      const int g = ok ? t / 96 : 0, r = ok ? t - g * 96 : 0, sec = r >> 5, pr = r & 31;
-      const int c = sec * d + h * HD + 2 * pr;
-      src[j] = p.partial + (long long)(row0 + g) * N + c;
-      acc[j] = ok ? __ldg(reinterpret_cast<const float2*>(p.bias + c)) : make_float2(0.f, 0.f);
-      slot[j] = ok && sec != 0 ? p.slot[row0 + g] : 0;
-    }
-#pragma unroll 2
-    for (int s2 = 0; s2 < p.n_splits; ++s2) {  // (slab order, as split_finalize does)
-      float2 a[TASKS];
+    for (int u = 0; u < 16; ++u)
+      if (i + u < hist) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)s_tab[i + u] * d);
 #pragma unroll
-      for (int j = 0; j < TASKS; ++j)
-        if (tid + j * NT < n_live * 96) a[j] = *reinterpret_cast<const float2*>(src[j] + s2 * p.split_stride);
-#pragma unroll
-      for (int j = 0; j < TASKS; ++j)
-        if (tid + j * NT < n_live * 96) { acc[j].x += a[j].x; acc[j].y += a[j].y; }
-    }
-#pragma unroll
-    for (int j = 0; j < TASKS; ++j) {
-      const int t = tid + j * NT;
-      if (t < n_live * 96) {
-        const int g = t / 96, r = t - g * 96, sec = r >> 5, pr = r & 31;
-        const __nv_bfloat162 r2 = __floats2bfloat162_rn(acc[j].x, acc[j].y);
-        const float2 f = __bfloat1622float2(r2);
-        const int dim = 2 * pr;
-        if (sec == 0) {
-          s_q[g][dim] = f.x * p.scale; s_q[g][dim + 1] = f.y * p.scale;
-        } else if (sec == 1) {
-          *reinterpret_cast<__nv_bfloat162*>(p.kpool + (long long)slot[j] * d + h * HD + dim) = r2;
-          s_k[g][dim] = f.x; s_k[g][dim + 1] = f.y;
-        } else {
-          *reinterpret_cast<__nv_bfloat162*>(p.vpool + (long long)slot[j] * d + h * HD + dim) = r2;
-          s_v[g][dim] = f.x; s_v[g][dim + 1] = f.y;
-        }
+    for (int u = 0; u < 16; ++u)
+      if (i + u < hist) {
+        const float2 f = __bfloat1622float2(v[u]);
+        acc.x = fmaf(sc[i + u], f.x, acc.x);
+        acc.y = fmaf(sc[i + u], f.y, acc.y);
       }
-    }
   }
-  __syncthreads();
-
-  // ---- B: page tables
-  int hist_r[GM];
-  int max_hist = 0, min_hist = 0x7fffffff, first = 0;
-  unsigned has = 0;  // rows with a history
-#pragma unroll
-  for (int g = GM - 1; g >= 0; --g) {
-    hist_r[g] = s_hist[g];
-    max_hist = max(max_hist, hist_r[g]);
-    if (hist_r[g] > 0) { min_hist = min(min_hist, hist_r[g]); first = g; has |= 1u << g; }
-  }
-  {
-    const int mh = max(max_hist, 1), tot = n_live * mh;
-    for (int base = tid; base < tot; base += NT * UB) {
-      int v[UB];
-#pragma unroll
-      for (int u = 0; u < UB; ++u) {
-        const int idx = base + u * NT;
-        if (idx < tot) {
-          const int g = idx / mh, i = idx - g * mh;
-          if (i < s_hist[g]) v[u] = p.table[(long long)s_trow[g] * p.table_stride + i];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UB; ++u) {
-        const int idx = base + u * NT;
-        if (idx < tot) {
-          const int g = idx / mh, i = idx - g * mh;
-          if (i < s_hist[g]) s_tab[g * ML + i] = v[u];
-        }
-      }
-    }
-  }
-  // the common prefix is only used when every row with a history has the same length (true in a beam step)
-  const bool uniform = min_hist == max_hist;
-  if (tid == 0) s_common = uniform ? max_hist : 0;
-  __syncthreads();
-
-  // ---- C: common prefix
-  if (uniform && (has & (has - 1))) {
-    for (int i = tid; i < max_hist; i += NT) {
-      const int ref = s_tab[first * ML + i];
-      bool same = true;
-#pragma unroll
-      for (int g = 0; g < GM; ++g)
-        if (((has >> g) & 1u) && s_tab[g * ML + i] != ref) same = false;
-      if (!same) { atomicMin(&s_common, i); break; }  // later positions of this thread are farther: done
-    }
-  }
-  __syncthreads();
-  const int common = s_common;
-  // items: [0, common) shared positions, then per row its tail [tail0, hist] (the own position included)
-  int toff[GM + 1];
-  toff[0] = common;
-#pragma unroll
-  for (int g = 0; g < GM; ++g) {
-    const int tail0 = hist_r[g] > 0 ? common : 0;
-    toff[g + 1] = toff[g] + (hist_r[g] >= 0 ? hist_r[g] - tail0 + 1 : 0);
-  }
-  const int n_items = toff[GM];
-  // item -> (position, rows, a row to take the page table from)
-  auto decode = [&](int idx, int& i, unsigned& rows, int& g1) {
-    if (idx < common) { i = idx; rows = has; g1 = first; return; }
-    i = 0; rows = 0; g1 = 0;
-#pragma unroll
-    for (int g = 0; g < GM; ++g)
-      if (idx >= toff[g] && idx < toff[g + 1]) {
-        i = idx - toff[g] + (hist_r[g] > 0 ? common : 0);
-        rows = 1u << g;
-        g1 = g;
-      }
-  };
-
-  // ---- D: scores, one thread per item
-  for (int it = tid; it < n_items; it += NT) {
-    int i, g1;
-    unsigned rows;
-    decode(it, i, rows, g1);
-    float kf[HD];
-    if (i < s_hist[g1]) {
-      const long long roff = (long long)s_tab[g1 * ML + i] * d + h * HD;
-      const uint4* kp = reinterpret_cast<const uint4*>(p.kpool + roff);
-      uint4 kr[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) kr[c] = __ldg(kp + c);
-      // the value row of the same position is needed right after the softmax: start pulling it into L2
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.vpool + roff));
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&kr[c]);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 f = __bfloat1622float2(u2[t]);
-          kf[8 * c + 2 * t] = f.x; kf[8 * c + 2 * t + 1] = f.y;
-        }
-      }
-    } else {  // the row's own key
-#pragma unroll
-      for (int c = 0; c < HD; c += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(&s_k[g1][c]);
-        kf[c] = a.x; kf[c + 1] = a.y; kf[c + 2] = a.z; kf[c + 3] = a.w;
-      }
-    }
-    auto dot = [&](int g) {
-      float acc = 0.f;
-#pragma unroll
-      for (int c = 0; c < HD; c += 4) {
-        const float4 q4 = *reinterpret_cast<const float4*>(&s_q[g][c]);
-        acc = fmaf(q4.x, kf[c], acc); acc = fmaf(q4.y, kf[c + 1], acc);
-        acc = fmaf(q4.z, kf[c + 2], acc); acc = fmaf(q4.w, kf[c + 3], acc);
-      }
-      sc[g * ML + i] = acc;
-    };
-    if (it < common) {
-#pragma unroll
-      for (int g = 0; g < GM; ++g)
-        if ((has >> g) & 1u) dot(g);
-    } else {
-      dot(g1);
-    }
-  }
-  __syncthreads();
-
-  // ---- E: softmax, one warp per row
-  for (int g = warp; g < n_live; g += NW) {
-    float* scg = sc + g * ML;
-    const int hist = s_hist[g];
-    float mx = -INFINITY;
-    for (int i = lane; i <= hist; i += 32) mx = fmaxf(mx, scg[i]);
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int i = lane; i < hist; i += 32) {
-      const float e = __expf(scg[i] - mx);
-      scg[i] = e;
-      sum += e;
-    }
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float p_own = __expf(scg[hist] - mx);
-    __syncwarp();
-    if (lane == 0) { scg[hist] = p_own; s_inv[g] = 1.0f / (sum + p_own); }
-  }
-  __syncthreads();
-
-  // ---- F: P.V
-  {
-    float2 acc[GM];
-#pragma unroll
-    for (int g = 0; g < GM; ++g) acc[g] = make_float2(0.f, 0.f);
-    const bf16* vl = p.vpool + h * HD + 2 * lane;
-    {
-      const int* tab = s_tab + first * ML;
-      for (int i0 = warp; i0 < common; i0 += UB * NW) {
-        __nv_bfloat162 v[UB];
-#pragma unroll
-        for (int u = 0; u < UB; ++u) {
-          const int i = i0 + u * NW;
-          if (i < common) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)tab[i] * d);
-        }
-#pragma unroll
-        for (int u = 0; u < UB; ++u) {
-          const int i = i0 + u * NW;
-          if (i < common) {
-            const float2 f = __bfloat1622float2(v[u]);
-#pragma unroll
-            for (int g = 0; g < GM; ++g)
-              if ((has >> g) & 1u) {
-                const float pw = sc[g * ML + i];
-                acc[g].x = fmaf(pw, f.x, acc[g].x);
-                acc[g].y = fmaf(pw, f.y, acc[g].y);
-              }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < GM; ++g) {
-      const int hist = hist_r[g];
-      if (hist >= 0) {
-        const int* tab = s_tab + g * ML;
-        for (int i0 = (hist > 0 ? common : 0) + warp; i0 < hist; i0 += 4 * NW) {
-          __nv_bfloat162 v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * NW;
-            if (i < hist) v[u] = *reinterpret_cast<const __nv_bfloat162*>(vl + (long long)tab[i] * d);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * NW;
-            if (i < hist) {
-              const float2 f = __bfloat1622float2(v[u]);
-              const float pw = sc[g * ML + i];
-              acc[g].x = fmaf(pw, f.x, acc[g].x);
-              acc[g].y = fmaf(pw, f.y, acc[g].y);
-            }
-          }
-        }
-        if (warp == (g % NW)) {  // the row's own value
-          const float pw = sc[g * ML + hist];
-          acc[g].x = fmaf(pw, s_v[g][2 * lane], acc[g].x);
-          acc[g].y = fmaf(pw, s_v[g][2 * lane + 1], acc[g].y);
-        }
-      }
-      *reinterpret_cast<float2*>(&s_acc[warp][g][2 * lane]) = acc[g];
-    }
-  }
-  __syncthreads();
-  for (int t = tid; t < n_live * 32; t += NT) {
-    const int g = t >> 5, pr = t & 31;
-    float2 o = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const float2 a = *reinterpret_cast<const float2*>(&s_acc[w][g][2 * pr]);
-      o.x += a.x; o.y += a.y;
-    }
-    const float inv = s_inv[g];
-    bf16* op = p.out + (long long)(row0 + g) * p.out_stride + h * HD + 2 * pr;
-    *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(o.x * inv, o.y * inv);
-  }
+  bf16* op = p.out + (long long)qi * p.out_stride + h * HD + 2 * lane;
+  *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
 }
 
 void qkv_attention(const QkvAttnParams& p, int n_rows, int n_heads, cudaStream_t stream) {
   if (n_rows <= 0) return;
-  B200W_REQUIRE(p.d == n_heads * HD, "qkv_attention: head dim 64");
-  QkvAttnParams q = p;
-  int G = p.rows_per_cta;
-  static const char* g_env = getenv("B200W_QKV_ROWS");
-  if (g_env) G = atoi(g_env);
-  G = std::max(1, std::min(G, QG_MAX_ROWS));
-  q.rows_per_cta = G;
-  q.n_rows = n_rows;
-  const size_t smem = (size_t)2 * G * p.max_len * sizeof(float);
-  const dim3 grid(cdiv(n_rows, G), n_heads);
-  if (G == 1) {
-    ensure_dynamic_smem(qkv_attn_kernel<128, 1, 6>, smem);
-    launch_pdl(qkv_attn_kernel<128, 1, 6>, grid, dim3(128), smem, stream, q);
-  } else if (G <= 5) {
-    ensure_dynamic_smem(qkv_attn_kernel<128, 5, 5>, smem);
-    launch_pdl(qkv_attn_kernel<128, 5, 5>, grid, dim3(128), smem, stream, q);
-  } else {
-    ensure_dynamic_smem(qkv_attn_kernel<128, 8, 4>, smem);
-    launch_pdl(qkv_attn_kernel<128, 8, 4>, grid, dim3(128), smem, stream, q);
-  }
+  B200W_REQUIRE(n_heads % 4 == 0 && p.d == n_heads * HD, "qkv_attention: heads must be a multiple of 4, head dim 64");
+  const size_t smem = (size_t)(1 + 4) * p.max_len * sizeof(float);
+  launch_pdl(qkv_attn_kernel, dim3(n_rows, n_heads / 4), dim3(128), smem, stream, p);
   B200W_COUNT_LAUNCH();
   B200W_CHECK_CUDA(cudaGetLastError());
 }

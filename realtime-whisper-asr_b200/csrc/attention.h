@@ -55,8 +55,6 @@ struct QkvAttnParams {
   int out_stride = 0;
   float scale = 0.125f;
   int max_len = 0;
-  int rows_per_cta = 1;  // consecutive rows of one stream (its beams) handled by one CTA, one warp each (<= 8)
-  int n_rows = 0;        // set by the launcher
 };
 void qkv_attention(const QkvAttnParams& p, int n_rows, int n_heads, cudaStream_t stream);
 

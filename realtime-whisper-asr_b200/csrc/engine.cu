@@ -193,7 +193,6 @@ struct b200w_engine {
   std::vector<StepGraph> step_graphs;
   bool use_graphs = true;
   bool step_pass = false;  // the pass being enqueued is a decode step (selects the skinny GEMM path)
-  int step_rows_per_stream = 1;  // decode steps: rows r = b*K + k, i.e. K consecutive rows per stream
   unsigned long long launches_per_step = 0;
   cudaStream_t own_stream = nullptr;  // decode runs here (the legacy default stream cannot be captured)
   cudaEvent_t join_event = nullptr;
@@ -487,7 +486,7 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
     const bool sk = use_skinny() && e->step_pass && d % 128 == 0;
     // reduction of the QKV slabs + cache write + self-attention in one kernel (needs heads % 4 == 0)
     static const bool use_fused = getenv("B200W_NO_FUSED_ATTN") == nullptr;
-    const bool fused_attn = sk && use_fused && !((ablate_mask() >> 2) & 1u);
+    const bool fused_attn = sk && use_fused && e->H % 4 == 0 && !((ablate_mask() >> 2) & 1u);
     if (sk) {
       // split-K QKV projection; the reduction adds the bias, rounds to bf16 and scatters K / V into the cache
       RUN(2) {
@@ -499,7 +498,6 @@ void decoder_forward(b200w_engine* e, const bf16* cross_kv, const PassMeta& m, c
           qa.slot = m.slot; qa.kpool = kp; qa.vpool = vp;
           qa.table = table; qa.table_stride = e->Tctx; qa.trow = m.trow; qa.kvlen = m.kvlen;
           qa.out = attn; qa.out_stride = d; qa.scale = 0.125f; qa.max_len = max_kvlen;
-          qa.rows_per_cta = e->step_rows_per_stream;
           qkv_attention(qa, n, e->H, s);
         } else {
           split_finalize(r.partial, r.n, r.stride, r.bias, n, 3 * d, 0, qkv, 3 * d, m.slot, kp, vp, d, s);
@@ -696,7 +694,6 @@ void decoder_step_fused(b200w_engine* e, const bf16* cross_kv, const PassMeta& m
       qa.slot = m.slot; qa.kpool = kp; qa.vpool = vp;
       qa.table = table; qa.table_stride = e->Tctx; qa.trow = m.trow; qa.kvlen = m.kvlen;
       qa.out = attn; qa.out_stride = d; qa.scale = 0.125f; qa.max_len = max_kvlen;
-      qa.rows_per_cta = e->step_rows_per_stream;
       qkv_attention(qa, n, e->H, s);
     }
     RUN(6) {
@@ -1176,7 +1173,6 @@ int b200w_decode(b200w_engine* e, const void* cross_kv_dev, int B, const int32_t
     gather_fork_tables(e->tables[from].as<int>(), m.parent, m.trow, m.pos, m.slot, e->tables[from ^ 1].as<int>(),
                        m.n, Tctx, s);
     e->step_pass = true;
-    e->step_rows_per_stream = K;
     try {
       if (fused_step_ok(e, m.n) && m.max_group <= CROSS_GROUP && m.n_groups <= 64) {
         decoder_step_fused(e, ckv, m, e->tables[from ^ 1].as<int>(), Tctx, s);

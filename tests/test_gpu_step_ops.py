@@ -81,13 +81,13 @@ def _self_attention_case(lib, dev, H, G, n_streams, hist, shared, n_splits, idle
 
 
 @pytest.mark.parametrize("H,G,n_streams,hist,shared,n_splits,idle,ragged", [
-    (6, 1, 5, 37, 37, 4, (), False),          # greedy: one row per stream
-    (6, 5, 4, 100, 80, 4, (), False),         # beams sharing most of their history
+    (8, 1, 5, 37, 37, 4, (), False),          # greedy: one row per stream
+    (8, 5, 4, 100, 80, 4, (), False),         # beams sharing most of their history
     (20, 5, 32, 130, 110, 4, (7, 8, 9), False),  # the bench shape, one stream partly idle
-    (6, 5, 3, 64, 0, 2, (), False),           # nothing shared
-    (6, 5, 3, 1, 1, 1, (), False),
-    (6, 5, 3, 0, 0, 4, (), False),            # first step after an empty prompt: only the own position
-    (8, 8, 3, 300, 290, 3, (0,), True),       # widest group, ragged histories (no common-prefix path), short last group
+    (4, 5, 3, 64, 0, 2, (), False),           # nothing shared
+    (8, 5, 3, 1, 1, 1, (), False),
+    (8, 5, 3, 0, 0, 4, (), False),            # first step after an empty prompt: only the own position
+    (8, 8, 3, 300, 290, 3, (0,), True),       # ragged histories, short last group
     (12, 3, 7, 33, 20, 5, (4,), True),
 ])
 def test_step_self_attention(lib, cuda_device, H, G, n_streams, hist, shared, n_splits, idle, ragged):

@@ -12,7 +12,8 @@ NCU="ncu --set full --clock-control none --import-source on --profile-from-start
 $NCU -k regex:cross_attn_sp_kernel -s 40 -c 2 -o gpurun_out/ncu_cross_sp_$TAG -f $CMD > /dev/null 2>&1
 $NCU -k regex:skinny_gemm_kernel -s 200 -c 6 -o gpurun_out/ncu_skinny_$TAG -f $CMD > /dev/null 2>&1
 $NCU -k regex:gemm_tcgen05_kernel -s 20 -c 4 -o gpurun_out/ncu_gemm_enc_$TAG -f $CMD > /dev/null 2>&1
-$NCU -k regex:enc_attn_kernel -s 2 -c 1 -o gpurun_out/ncu_enc_attn_$TAG -f $CMD > /dev/null 2>&1
+$NCU -k regex:enc_attn -s 2 -c 1 -o gpurun_out/ncu_enc_attn_$TAG -f $CMD > /dev/null 2>&1
 $NCU -k regex:qkv_attn_kernel -s 40 -c 1 -o gpurun_out/ncu_qkv_attn_$TAG -f $CMD > /dev/null 2>&1
+$NCU -k regex:sample_row_kernel -s 2 -c 1 -o gpurun_out/ncu_sample_row_$TAG -f $CMD > /dev/null 2>&1
 $NCU -k regex:logmel_kernel -c 1 -o gpurun_out/ncu_logmel_$TAG -f $CMD > /dev/null 2>&1
 ls -la gpurun_out/*_$TAG.ncu-rep gpurun_out/launches_$TAG.csv

@@ -53,7 +53,7 @@ def attention_case(hist, shared):
     out = torch.zeros(rows, d, dtype=torch.bfloat16, device=dev)
     table, slot, kvlen, trow = (t.to(dev) for t in (table, slot, kvlen, trow))
     res = {}
-    for name, code in (("G=1", 1), ("G=5", 5)):
+    for name, code in (("row per warp", 1),):
         def run():
             for kp, vp in pools:
                 _lib.check(lib.b200w_step_self_attention(partial.data_ptr(), NS, bias.data_ptr(), rows, d, H,
