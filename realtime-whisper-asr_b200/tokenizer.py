@@ -160,9 +160,15 @@ class Tokenizer:
         decoded_full = self.decode_with_timestamps(tokens)
         rc = "�"
         words, word_tokens, current, offset = [], [], [], 0
+        single = self.__dict__.setdefault("_single_token_text", {})  # most units are one token: decode each id once
         for token in tokens:
             current.append(token)
-            decoded = self.decode_with_timestamps(current)
+            if len(current) == 1:
+                decoded = single.get(token)
+                if decoded is None:
+                    decoded = single[token] = self.decode_with_timestamps(current)
+            else:
+                decoded = self.decode_with_timestamps(current)
             try:
                 idx = offset + decoded.index(rc)
                 incomplete = decoded_full[idx] != rc if idx < len(decoded_full) else True

@@ -211,7 +211,10 @@ def words_from_alignment(tokenizer: Tokenizer, text_tokens: List[int], text_indi
     jump_times = time_indices[jumps] / TOKENS_PER_SECOND
     start_times = jump_times[word_boundaries[:-1]]
     end_times = jump_times[word_boundaries[1:]]
-    probs = [float(np.mean(text_token_probs[i:j])) for i, j in zip(word_boundaries[:-1], word_boundaries[1:])]
+    # (plain Python sums: np.mean on 1-3 element slices costs ~7 us per word, ~1600 words per bench step)
+    tp = text_token_probs.tolist()
+    probs = [(sum(tp[i:j]) / (j - i)) if j > i else float("nan")
+             for i, j in zip(word_boundaries[:-1].tolist(), word_boundaries[1:].tolist())]
     return [dict(word=w, tokens=t, start=float(s), end=float(e), probability=p)
             for w, t, s, e, p in zip(words, word_tokens, start_times, end_times, probs)]
 
