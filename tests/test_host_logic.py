@@ -107,3 +107,54 @@ def test_no_cpu_fallback():
     if not torch.cuda.is_available():
         with pytest.raises(_lib.B200WError):
             B200WhisperModel("tiny", device="cuda")
+
+
+def test_temperature_fallback_ladder_host_logic():
+    """transcribe._decode_with_fallback against faster-whisper's generate_with_fallback rules, with a scripted engine
+    (no GPU): which chunks are decoded again at which temperature, which result each chunk keeps."""
+    import types
+
+    import torch
+
+    from realtime_whisper_asr_b200.engine import DecodeResult
+    from realtime_whisper_asr_b200.transcribe import B200WhisperModel, TranscriptionOptions
+
+    tk = Tokenizer(51865, True, language="en")
+    good = tk.encode(" the quick brown fox jumps over the lazy dog")
+    rep = tk.encode(" la" * 60)  # compression ratio far above 2.4
+
+    def res(tokens, avg_logprob, no_speech=0.0):
+        return DecodeResult(list(tokens), avg_logprob * (len(tokens) + 1), no_speech)
+
+    # script[temperature][chunk] -> result
+    script = {
+        0.0: [res(good, -0.2), res(rep, -0.3), res(good, -1.5), res(good, -2.0, no_speech=0.9), res(rep, -0.9)],
+        0.4: [None, res(good, -0.5), res(good, -1.4), None, res(rep, -0.5)],
+        0.8: [None, None, res(good, -1.2), None, res(rep, -0.7)],
+    }
+    calls = []
+
+    class Engine:
+        def decode(self, ckv, prompts, opts):
+            idx = [int(p[0]) for p in prompts]  # the prompt carries the chunk's index
+            calls.append((round(opts.temperature, 3), idx, opts.best_of))
+            assert ckv.shape[0] == len(prompts)
+            return [script[round(opts.temperature, 3)][i] for i in idx]
+
+    fake = types.SimpleNamespace(_sample_seed=0, max_beam=5, tokenizer=lambda lang, task="transcribe": tk,
+                                 suppress_ids=None, suppress_ids_begin=None)
+    fake._decode_options = types.MethodType(B200WhisperModel._decode_options, fake)
+    o = TranscriptionOptions(5, 3, 1.0, 1.0, 1.0, 0, -1.0, 0.6, 2.4, True, 0.5, [0.0, 0.4, 0.8], None, None, True, [-1],
+                             False, 1.0, False, "", "", None)
+    batch = [types.SimpleNamespace(prompt=[i], tokenizer=tk) for i in range(5)]
+    ckv = torch.zeros(5, 1)
+    final, temps = B200WhisperModel._decode_with_fallback(fake, Engine(), ckv, batch, o)
+    # rung 0: everything; rung 0.4: the repetitive (1, 4) and the unlikely (2) chunks -- not the silent one (3);
+    # rung 0.8: what still fails
+    assert calls == [(0.0, [0, 1, 2, 3, 4], 3), (0.4, [1, 2, 4], 3), (0.8, [2, 4], 3)]
+    assert temps[0] == 0.0 and final[0] is script[0.0][0]
+    assert temps[1] == 0.4 and final[1] is script[0.4][1]           # fixed by the first fallback
+    assert temps[3] == 0.0 and final[3] is script[0.0][3]           # silence: low log-probability is not a failure
+    assert temps[2] == 0.8 and final[2] is script[0.8][2]           # failed everywhere: best average log-probability
+    assert temps[4] == 0.4 and final[4] is script[0.4][4]           # all above the compression threshold: best of all
+    assert fake._sample_seed == 3                                    # one seed per decode call
