@@ -42,6 +42,28 @@ int num_sms() {
   return n;
 }
 
+void* alloc_descriptor_record(size_t bytes) {
+  static std::mutex mu;
+  static char* chunk[64] = {nullptr};
+  static size_t used[64] = {0};
+  constexpr size_t CHUNK = 1 << 20;
+  bytes = (bytes + 127) & ~static_cast<size_t>(127);
+  B200W_REQUIRE(bytes <= CHUNK, "descriptor record too large");
+  int dev = 0;
+  B200W_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  const int s = dev & 63;
+  if (!chunk[s] || used[s] + bytes > CHUNK) {
+    void* p = nullptr;
+    B200W_CHECK_CUDA(cudaMalloc(&p, CHUNK));  // (the previous chunk stays allocated: its records are in use)
+    chunk[s] = static_cast<char*>(p);
+    used[s] = 0;
+  }
+  void* r = chunk[s] + used[s];
+  used[s] += bytes;
+  return r;
+}
+
 void ensure_dynamic_smem(const void* func, size_t bytes) {
   static std::mutex mu;
   static std::map<std::pair<int, const void*>, size_t> done;

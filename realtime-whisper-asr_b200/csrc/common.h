@@ -57,6 +57,12 @@ struct Error : public std::runtime_error {
   return 0;
 
 int num_sms();  // SM count of the CURRENT device (cached per device)
+// Device memory for records that hold TMA descriptors (CUtensorMap) read by kernels from GLOBAL memory.  The address
+// of such a record is never given out twice in the life of the process: the TMA unit caches descriptors by address,
+// and a record freed by one engine and re-allocated (same address, other contents) by the next was fetched stale --
+// an intermittent illegal memory access once engines had been destroyed and created (round 2: 2 of ~30 runs of the
+// GPU suite).  Bump allocation from chunks that are never freed; ~0.5 KB per distinct decode GEMM call.
+void* alloc_descriptor_record(size_t bytes);
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per (device, function): remember what each device was given
 // (grow-only) instead of a per-process flag, so engines on several GPUs of one process all get configured.
 void ensure_dynamic_smem(const void* func, size_t bytes);

@@ -482,7 +482,6 @@ struct DstepCache {
 DstepCache* dstep_cache_create() { return new DstepCache(); }
 void dstep_cache_destroy(DstepCache* c) {
   if (!c) return;
-  for (auto& kv : c->recs) cudaFree(kv.second.dev);
   if (c->bar) cudaFree(c->bar);
   delete c;
 }
@@ -548,8 +547,9 @@ void dstep_run(DstepCache* cache, int key, const DsPhaseDesc* phases, int n_phas
     if (host.stages > DS_MAX_STAGES) host.stages = DS_MAX_STAGES;
     host.bar = cache->bar;
     host.trace = (key % 128) == g_ds_trace_key ? g_ds_trace : nullptr;
-    if (!rec.dev) B200W_CHECK_CUDA(cudaMalloc(&rec.dev, sizeof(DsLaunch)));
-    // (a record is only rebuilt when its call site changes shape, never inside a captured decode step)
+    // (a record is only rebuilt when its call site changes shape, never inside a captured decode step; a rebuilt
+    // record gets a NEW address: descriptors are cached by address)
+    rec.dev = static_cast<DsLaunch*>(alloc_descriptor_record(sizeof(DsLaunch)));
     B200W_CHECK_CUDA(cudaMemcpyAsync(rec.dev, &host, sizeof(host), cudaMemcpyHostToDevice, stream));
     B200W_CHECK_CUDA(cudaStreamSynchronize(stream));
     rec.desc_bytes.assign(reinterpret_cast<const unsigned char*>(phases), reinterpret_cast<const unsigned char*>(phases) + nbytes);

@@ -47,8 +47,9 @@ __device__ __forceinline__ long long sk_gtime() { long long t; asm volatile("mov
 // block with a single coalesced load and lets the TMA unit read the descriptors from the same
 // record (measured 1.9 us faster per launch than a 350-byte kernel-parameter block, which lives in
 // the constant bank and is cold in every freshly launched CTA).  Records are created once per
-// distinct call (a decode step repeats the same calls on the same buffers) and live in a SkinnyCache
-// that its owner (an engine) frees.
+// distinct call (a decode step repeats the same calls on the same buffers) and are indexed by a SkinnyCache that
+// its owner (an engine) frees; the records themselves come from alloc_descriptor_record(): their addresses are
+// never reused (the TMA unit caches descriptors by address).
 struct __align__(128) SkinnyLaunch {
   CUtensorMap tmW, tmX;
   SkinnyParams p;
@@ -244,8 +245,7 @@ struct SkinnyCache {
 SkinnyCache* skinny_cache_create() { return new SkinnyCache(); }
 void skinny_cache_destroy(SkinnyCache* c) {
   if (!c) return;
-  for (auto& kv : c->recs) cudaFree(kv.second);
-  delete c;
+  delete c;  // (the records stay: see alloc_descriptor_record)
 }
 static SkinnyCache* default_cache() {
   static SkinnyCache* per_dev[64] = {nullptr};
@@ -310,16 +310,13 @@ void skinny_gemm(const SkinnyDesc& d, cudaStream_t stream) {
   auto it = cache->recs.find(key);
   if (it == cache->recs.end()) {
     if (!d.cache && cache->recs.size() >= 512) {  // the shared default is bounded: drop everything once idle
-      B200W_CHECK_CUDA(cudaDeviceSynchronize());
-      for (auto& kv : cache->recs) cudaFree(kv.second);
-      cache->recs.clear();
+      cache->recs.clear();  // (the records themselves are never freed nor reused: see alloc_descriptor_record)
     }
     SkinnyLaunch host;
     host.tmW = tmW;
     host.tmX = tmX;
     host.p = p;
-    SkinnyLaunch* devrec = nullptr;
-    B200W_CHECK_CUDA(cudaMalloc(&devrec, sizeof(SkinnyLaunch)));
+    SkinnyLaunch* devrec = static_cast<SkinnyLaunch*>(alloc_descriptor_record(sizeof(SkinnyLaunch)));
     B200W_CHECK_CUDA(cudaMemcpy(devrec, &host, sizeof(host), cudaMemcpyHostToDevice));
     it = cache->recs.emplace(key, devrec).first;
   }
