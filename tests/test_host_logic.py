@@ -158,3 +158,27 @@ def test_temperature_fallback_ladder_host_logic():
     assert temps[2] == 0.8 and final[2] is script[0.8][2]           # failed everywhere: best average log-probability
     assert temps[4] == 0.4 and final[4] is script[0.4][4]           # all above the compression threshold: best of all
     assert fake._sample_seed == 3                                    # one seed per decode call
+
+
+def test_words_from_alignment_matches_the_numpy_statement():
+    """transcribe.words_from_alignment (faster-whisper find_alignment after the DTW): the word probabilities are the
+    means of their tokens' probabilities (plain Python sums since round 2), times come from the path's jumps."""
+    rng = np.random.default_rng(3)
+    tk = Tokenizer(51865, True, language="en")
+    text = tk.encode(" hello world, this is a test of word timing.")
+    n = len(text) + 1  # + EOT, as the aligner sees it
+    frames = np.sort(rng.integers(0, 400, size=n)).astype(np.int64)
+    text_indices = np.repeat(np.arange(n), 3)
+    time_indices = np.repeat(frames, 3) + np.tile(np.arange(3), n)
+    probs = rng.random(n - 1).astype(np.float32)
+    words = T.words_from_alignment(tk, text, text_indices, time_indices, probs)
+    w_text, w_tokens = tk.split_to_word_tokens(text + [tk.eot])
+    assert [w["word"] for w in words] == w_text[:-1] and [w["tokens"] for w in words] == w_tokens[:-1]
+    bounds = np.pad(np.cumsum([len(t) for t in w_tokens[:-1]]), (1, 0))
+    jumps = np.pad(np.diff(text_indices), (1, 0), constant_values=1).astype(bool)
+    jump_times = time_indices[jumps] / 50.0
+    for k, w in enumerate(words):
+        assert w["start"] == pytest.approx(jump_times[bounds[k]]) and w["end"] == pytest.approx(jump_times[bounds[k + 1]])
+        assert w["probability"] == pytest.approx(float(np.mean(probs[bounds[k]:bounds[k + 1]])), rel=1e-6)
+    # the cached single-token decodes give the same split as a fresh tokenizer
+    assert Tokenizer(51865, True, language="en").split_to_word_tokens(text + [tk.eot]) == (w_text, w_tokens)
